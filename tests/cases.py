@@ -1,0 +1,139 @@
+"""Shared test-case definitions: the same dicts drive tools/make_golden.py (real reference, build
+container), the CPU oracle tests and the GPU parity tests.  Inputs are regenerated from seeds."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import synth
+
+GRID_KW = dict(seed=5, shape=(42, 42, 22), occupancy=0.6, voxel_size=0.05)
+
+_BASE = dict(n_rays=48, n_samples=64, n_importance=64, use_voxel=True, use_disp=False, perturb=0.0,
+             noise_std=0.0, white_back=False, forward_instance=True, frustum_bound_th=0.0,
+             rays_in_bbox=False, is_eval=True, pass_through=False, sigma_gain=8.0, sigma_bias=1.0,
+             seed=100)
+
+RENDER_CASES = {
+    # BASELINE.json configs[0]: single 64-ray chunk, 64 coarse samples, scene branch only
+    "cfg1_plain": dict(_BASE, n_rays=64, n_importance=0, use_voxel=False, forward_instance=False, seed=101),
+    "cfg1_voxel": dict(_BASE, n_rays=64, n_importance=0, forward_instance=False, seed=102),
+    # configs[1]-like: 64 coarse + 64 importance (128-sample fine pass), two-branch, eval
+    "eval_voxel": dict(_BASE, seed=103),
+    "eval_plain": dict(_BASE, use_voxel=False, seed=104),
+    "eval_in_bbox": dict(_BASE, rays_in_bbox=True, seed=105),
+    "eval_white_disp": dict(_BASE, white_back=True, use_disp=True, n_rays=33, seed=106),
+    # configs[2]-like training-mode forward: jitter + sigma noise + occlusion mask + pass-through
+    "train_voxel": dict(_BASE, perturb=1.0, noise_std=1.0, is_eval=False, frustum_bound_th=0.025,
+                        pass_through=True, seed=107),
+    "train_nomask": dict(_BASE, perturb=1.0, noise_std=1.0, is_eval=False, frustum_bound_th=-1.0 / 16,
+                         seed=108, n_rays=17),
+    # ragged sizes / odd sample counts
+    "odd_sizes": dict(_BASE, n_rays=5, n_samples=40, n_importance=24, seed=109),
+    "one_ray": dict(_BASE, n_rays=1, seed=110),
+}
+
+MULTI_CASES = {
+    # configs[4]: scene + duplicated object (ids [0,4,4]), removed-object boxes on the scene branch
+    "edit_dup": dict(n_rays=40, n_samples=64, n_importance=64, obj_ids=[0, 4, 4], white_back=False,
+                     boxes=True, seed=200),
+    "edit_scene_only": dict(n_rays=16, n_samples=64, n_importance=64, obj_ids=[0], white_back=True,
+                            boxes=False, seed=201),
+    "edit_two_objs": dict(n_rays=24, n_samples=32, n_importance=32, obj_ids=[4, 6], white_back=False,
+                          boxes=False, seed=202),
+}
+
+
+def build_render_case(c):
+    s = c["seed"]
+    w = {"coarse": synth.make_weights(s, c["use_voxel"], c["sigma_gain"], c["sigma_bias"])}
+    if c["n_importance"] > 0:
+        w["fine"] = synth.make_weights(s + 1000, c["use_voxel"], c["sigma_gain"], c["sigma_bias"])
+    n = c["n_rays"]
+    rays = synth.random_rays(s + 1, n)
+    code_table = synth.make_codes(s + 2)
+    rng = np.random.default_rng(s + 3)
+    ids = rng.choice([4, 6], size=n)
+    codes = code_table[torch.from_numpy(ids)]
+    ptm = torch.from_numpy(rng.random((n, 1)) < 0.5) if c["pass_through"] else None
+    return {
+        "weights": w,
+        "grid": synth.make_grid(**GRID_KW) if c["use_voxel"] else None,
+        "rays": rays,
+        "codes": codes,
+        "pass_through_mask": ptm,
+        "rand": synth.random_buffers(s + 4, n, c["n_samples"], c["n_importance"]),
+    }
+
+
+def build_multi_case(c):
+    s = c["seed"]
+    n = c["n_rays"]
+    w = {"coarse": synth.make_weights(s, True, 8.0, 1.0), "fine": synth.make_weights(s + 1000, True, 8.0, 1.0)}
+    rng = np.random.default_rng(s + 5)
+    rays_list = []
+    for k, iid in enumerate(c["obj_ids"]):
+        rays = synth.random_rays(s + 10 + k, n) if k == 0 else rays_list[0].clone()
+        if iid > 0:
+            # object ray sets: per-ray near/far from a bbox hit; misses get near = far = 0
+            # (render_tools/editable_renderer.py:153-181)
+            near = torch.from_numpy(rng.uniform(0.4, 1.2, size=n).astype(np.float32))
+            far = near + torch.from_numpy(rng.uniform(0.2, 0.9, size=n).astype(np.float32))
+            miss = torch.from_numpy(rng.random(n) < 0.3)
+            near[miss] = 0
+            far[miss] = 0
+            rays = rays.clone()
+            rays[:, 0:3] += torch.from_numpy(rng.normal(0, 0.05, size=(1, 3)).astype(np.float32))
+            rays[:, 6], rays[:, 7] = near, far
+        rays_list.append(rays)
+    boxes = []
+    if c["boxes"]:
+        for b in range(2):
+            ang = 0.3 + 0.5 * b
+            A = np.eye(4)
+            A[:3, :3] = np.array([[np.cos(ang), -np.sin(ang), 0], [np.sin(ang), np.cos(ang), 0], [0, 0, 1]])
+            A[:3, 3] = np.array([0.1 * b, -0.2, 0.05])
+            P = np.eye(4)
+            P[:3, 3] = np.array([0.3, -0.1 * b, 0.0])
+            lo = np.array([-0.5, -0.4, -0.3]) + 0.1 * b
+            boxes.append(dict(scale_factor=2.0, pose_avg=P, axis_align_mat=A, bbox_bounds=np.array([lo, lo + 0.9])))
+    return {"weights": w, "grid": synth.make_grid(**GRID_KW), "rays_list": rays_list,
+            "code_table": synth.make_codes(s + 2), "boxes": boxes}
+
+
+def box_affine(b):
+    """Fold BBoxRayHelper.transform_xyz_to_bbox_coordinates (utils/bbox_utils.py:119-130: unscale,
+    pose_avg, axis_align) into p_box = A p + t; bounds from check_xyz_in_bounds with bbox_enlarge = 0."""
+    sf = b["scale_factor"]
+    P, Ax = b["pose_avg"], b["axis_align_mat"]
+    M = Ax[:3, :3] @ P[:3, :3]
+    A = M * sf
+    t = Ax[:3, :3] @ P[:3, 3] + Ax[:3, 3]
+    return (torch.from_numpy(A).float(), torch.from_numpy(t).float(),
+            torch.from_numpy(b["bbox_bounds"][0]).float(), torch.from_numpy(b["bbox_bounds"][1]).float())
+
+
+def stage_inputs():
+    rng = np.random.default_rng(7)
+    f = lambda a: torch.from_numpy(np.asarray(a, dtype=np.float32))
+    n = 96
+    g = synth.make_grid(**GRID_KW)
+    ext = (g["shape"].numpy() * float(g["voxel_size"]))
+    xyz = rng.uniform(-0.62, 0.62, size=(160, 3)) * ext  # inside and beyond the volume
+    wts = rng.random((n, 62)) ** 4
+    wts[:4] = 0.0            # all-zero rows (denominator guard)
+    wts[4:8, 10:] = 0.0      # empty tails
+    near = rng.uniform(0.1, 0.3, size=(n, 1))
+    bins = near + np.sort(rng.random((n, 63)), -1) * 2.5
+    return {
+        "posenc_x": f(rng.uniform(-3, 3, size=(64, 3))),
+        "voxel_xyz": f(xyz),
+        "emb_xyz_v": f(rng.uniform(-1, 1, size=(n, 271))),
+        "emb_xyz_p": f(rng.uniform(-1, 1, size=(n, 63))),
+        "emb_dir": f(rng.uniform(-1, 1, size=(n, 27))),
+        "obj_voxel": f(rng.uniform(-1, 1, size=(n, 104))),
+        "obj_code": f(rng.standard_normal((n, 64))),
+        "pdf_bins": f(bins),
+        "pdf_weights": f(wts),
+        "pdf_u": f(rng.random((n, 64))),
+    }
