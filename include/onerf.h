@@ -1,0 +1,179 @@
+/*
+ * onerf.h — C ABI of libonerf_sm100.so: the B200-native (sm_100a) per-ray render path of
+ * zju3dv/object_nerf (stratified + PDF sampling, positional / sparse-voxel encoding, the two-branch
+ * scene+object MLP, sigma->alpha front-to-back compositing, single-scene and multi-object variants).
+ *
+ * The reference has no FFI layer: its boundary is three Python functions.  This header
+ * is what a binding for that boundary calls; `object_nerf_b200/_lib.py` is the ctypes binding and
+ * INTEGRATION.md shows the reference-side stub.  Each entry point cites the reference code it replaces
+ * (paths relative to the reference root).
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer on the ctx's device unless the parameter name ends in `_host`;
+ *    the caller owns all buffers (inputs, outputs, workspace); fp32 row-major contiguous, 16-byte aligned;
+ *  - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises;
+ *  - every function returns 0 on success or a negative onerf_status; onerf_last_error() gives the
+ *    thread-local message.  Unsupported configurations are hard errors: there is no CPU fallback.
+ */
+#ifndef ONERF_H_
+#define ONERF_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ONERF_ABI_VERSION 1
+
+typedef enum onerf_status {
+  ONERF_OK = 0,
+  ONERF_ERR_BAD_ARG = -1,      /* null pointer / bad shape / misaligned buffer */
+  ONERF_ERR_UNSUPPORTED = -2,  /* configuration the kernels are not built for */
+  ONERF_ERR_CUDA = -3,         /* a CUDA runtime call failed */
+  ONERF_ERR_WORKSPACE = -4     /* caller-provided workspace too small */
+} onerf_status;
+
+/* arithmetic of the fused encode+MLP ("field") kernel */
+typedef enum onerf_precision {
+  ONERF_PREC_FP32 = 0, /* FFMA, fp32 throughout: verification / gradient-check mode */
+  ONERF_PREC_BF16 = 1  /* tcgen05 tensor cores: bf16 operands, fp32 accumulate in TMEM (product default) */
+} onerf_precision;
+
+typedef struct onerf_ctx onerf_ctx;
+
+int onerf_abi_version(void);
+const char* onerf_last_error(void);
+int onerf_ctx_create(int device, onerf_ctx** out);
+int onerf_ctx_destroy(onerf_ctx* ctx);
+/* number of kernels this ctx has launched since creation (bench.py's gpu_launches claim) */
+int64_t onerf_ctx_launch_count(const onerf_ctx* ctx);
+
+/* ---------------------------------------------------------------------------------------------
+ * Model weights.  One ObjectNeRF (models/nerf_model.py:18-95) = 20 nn.Linear layers, passed in this
+ * fixed order (W is [out,in] row-major fp32 exactly as nn.Linear stores it, b is [out]):
+ *   0..7  scene  xyz_encoding_1..8     8 scene.sigma   9 scene xyz_encoding_final
+ *   10    scene dir_encoding          11 scene rgb
+ *   12..15 object instance_encoding_1..4  16 instance_sigma  17 instance_encoding_final
+ *   18    inst_dir_encoding           19 inst_rgb
+ * Only the default architecture is built: D=8, W=256, skips=[4], inst_D=4, inst_W=128, inst_skips=[2],
+ * PE 10/4/6, 16+8 voxel channels, 64-long codes (config/default_conf.yml:7-36); use_voxel selects the
+ * 271/439-wide (voxel) or 63/127-wide (plain PE) inputs.  Anything else -> ONERF_ERR_UNSUPPORTED.
+ * ------------------------------------------------------------------------------------------- */
+#define ONERF_N_LINEAR 20
+
+size_t onerf_packed_weights_bytes(int use_voxel);
+/* Re-lay the 20 (W,b) pairs into the kernels' formats (fp32 K-major for the FFMA path; bf16, K-major,
+ * swizzled stage images in program order for the tcgen05 path).  Re-run whenever parameters change. */
+int onerf_pack_weights(onerf_ctx* ctx, int use_voxel, const float* const* W_host_ptrs,
+                       const float* const* b_host_ptrs, void* packed, size_t packed_bytes, void* stream);
+
+/* Sparse voxel grid: the buffers of EmbeddingVoxel the per-ray path reads
+ * (models/embedding_helper.py:107-133,189-200).  Metadata stays in device memory (the reference mutates
+ * it at epoch boundaries, :202-302) and is read by the kernels on every call. */
+typedef struct onerf_grid {
+  const float* table;         /* embedding_space_ftr.weight (n_rows, 24) */
+  const int64_t* idx_map;     /* voxel_idx_map (X,Y,Z) int64, -1 = empty */
+  const float* voxel_offset;  /* (3,) */
+  const float* voxel_size;    /* scalar */
+  const int64_t* voxel_shape; /* (3,) */
+} onerf_grid;
+
+/* ---------------------------------------------------------------------------------------------
+ * Stage entry points (each is also a step of onerf_render_rays_fwd)
+ * ------------------------------------------------------------------------------------------- */
+
+/* Stratified depths, models/rendering.py:259-277.  rays (N,8) = [o, d, near, far]; z_out (N,S).
+ * perturb > 0: jitter (N,S) U[0,1) is used if non-null, else drawn from Philox(seed). */
+int onerf_sample_coarse(onerf_ctx* ctx, const float* rays, int n_rays, int n_samples, int use_disp,
+                        float perturb, const float* jitter, uint64_t seed, float* z_out, void* stream);
+
+/* Inverse-CDF importance sampling + sorted merge with the coarse depths,
+ * models/rendering.py:11-61 and :301-313.  weights (N,S) are the full coarse weights (the [1:-1] slice
+ * and the mid-point bins are formed inside).  det != 0: u = linspace(0,1,K); else u (N,K) if non-null,
+ * else Philox(seed).  z_out (N, S+K) ascending. */
+int onerf_sample_pdf_merge(onerf_ctx* ctx, const float* z_coarse, const float* weights, int n_rays,
+                           int n_samples, int n_importance, int det, const float* u, uint64_t seed,
+                           float* z_out, void* stream);
+
+/* Stand-alone sample_pdf on explicit bins (N, n_bins) and weights (N, n_bins-1), the reference's exported
+ * helper models/rendering.py:11-61; out (N, K) in draw order (no merge). */
+int onerf_sample_pdf(onerf_ctx* ctx, const float* bins, const float* weights, int n_rays, int n_bins,
+                     int n_importance, int det, const float* u, uint64_t seed, float* out, void* stream);
+
+/* Encoding only (test / ncu entry): xyz (B,3) -> scene_in (B,271|63), obj_in (B,104) (null for plain
+ * PE).  models/embedding_helper.py:57-74, :325-411.  grid == NULL selects plain PE(10). */
+int onerf_encode(onerf_ctx* ctx, const onerf_grid* grid, const float* xyz, int64_t n_points,
+                 float* scene_in, float* obj_in, void* stream);
+
+/* Fused encode + two-branch MLP over all samples of a ray set,
+ * models/rendering.py:85-137 (+ models/nerf_model.py:97-152, models/embedding_helper.py:325-411),
+ * and render_tools/multi_rendering.py:16-93 for the one-branch-per-object editing variant. */
+typedef struct onerf_field_args {
+  const float* rays;       /* (N,8) */
+  const float* xyz;        /* optional explicit sample positions (N,S,3) (the inference_model() call
+                              surface, models/rendering.py:64-83); NULL -> o + d * z from rays */
+  const float* z;          /* sample depths: sample i of ray r at z[r * z_stride + i] */
+  int64_t z_stride;        /* >= S (S for a dense (N,S) array; n_obj*S inside a concatenated one) */
+  const float* codes;      /* (N,64) per-ray object codes (code_library lookup done by the caller,
+                              models/code_library.py:18-28), or NULL */
+  const float* code_row;   /* (64,) one code for every ray (editing path), used when codes == NULL */
+  int n_rays, n_samples;
+  const onerf_grid* grid;  /* NULL -> plain PE model */
+  const void* packed;      /* onerf_pack_weights output */
+  int want_scene, want_object;
+  int precision;           /* onerf_precision */
+  /* editing extras (render_tools/multi_rendering.py:40,83,92 and :239-241) */
+  int mute_zero_rays;      /* rays with z[:, -1] == 0 get sigma = -1e5 */
+  const float* boxes;      /* (n_boxes, 18): A row-major (9), t (3), lo (3), hi (3); scene samples with
+                              lo <= A p + t <= hi get sigma = -1e5 (utils/bbox_utils.py:119-130,158-207) */
+  int n_boxes;
+  float* scene_out;        /* float4 (rgb, sigma) of sample i of ray r at [r * out_stride + i]; iff want_scene */
+  float* obj_out;          /* same for the object branch; iff want_object */
+  int64_t out_stride;      /* >= S, in samples */
+  float* ray_const;        /* workspace, n_rays * ONERF_RAY_CONST_FLOATS floats */
+} onerf_field_args;
+#define ONERF_RAY_CONST_FLOATS 448
+
+int onerf_field_fwd(onerf_ctx* ctx, const onerf_field_args* args, void* stream);
+
+/* sigma->alpha->weights and front-to-back compositing of both branches, models/rendering.py:139-229. */
+typedef struct onerf_composite_args {
+  const float* z;          /* (N,S) */
+  const float* scene;      /* (N,S,4) rgb,sigma */
+  const float* obj;        /* (N,S,4) or NULL (forward_instance == False) */
+  int n_rays, n_samples;
+  float noise_std;
+  const float* noise_scene; /* (N,S) N(0,1) or NULL -> Philox(seed) when noise_std > 0 */
+  const float* noise_obj;
+  uint64_t seed;
+  int white_back, is_eval, zero_last_delta, rays_in_bbox;
+  float frustum_bound_th;
+  const uint8_t* pass_through_mask; /* (N,) or NULL */
+  float* weights;          /* (N,S)  (object weights if rays_in_bbox) */
+  float* opacity;          /* (N,) */
+  float* rgb;              /* (N,3) */
+  float* depth;            /* (N,) */
+  float* rgb_instance;     /* (N,3)  } */
+  float* depth_instance;   /* (N,)   } written iff obj != NULL */
+  float* opacity_instance; /* (N,)   } */
+} onerf_composite_args;
+
+int onerf_composite(onerf_ctx* ctx, const onerf_composite_args* args, void* stream);
+
+/* Joint depth sort over all objects' samples + compositing, render_tools/multi_rendering.py:96-157.
+ * Inputs are object-major: z_all (n_obj, N, S), field_all (n_obj, N, S, 4); the reference's concatenated
+ * sample index is c = obj * S + s, ties are kept in that order (stable sort).  Outputs in sorted order,
+ * (N, n_obj*S): z_sorted, weights, obj_ids (float list positions, or NULL); weights_unsorted
+ * (n_obj, N, S) = each object's weights back in its own sample order (what multi_rendering.py:269-271
+ * recovers with a boolean mask), or NULL.  Last delta is 0 (:125-128). */
+int onerf_composite_multi(onerf_ctx* ctx, const float* z_all, const float* field_all, int n_rays,
+                          int n_obj, int n_samples, int white_back, float* z_sorted, float* weights,
+                          float* obj_ids, float* weights_unsorted, float* opacity, float* rgb,
+                          float* depth, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ONERF_H_ */

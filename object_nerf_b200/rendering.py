@@ -1,0 +1,115 @@
+"""Drop-in for the reference's `models/rendering.py` call surface: render_rays(), inference_model(),
+sample_pdf() with identical signatures and result keys (reference models/rendering.py:11-17, 64-83,
+233-250).  Every stage runs as a CUDA kernel of libonerf_sm100.so; there is no PyTorch or CPU
+implementation behind these functions.
+
+Extra keyword-only knobs (absorbed by **dummy_kwargs in the reference, so call sites stay valid):
+  precision="bf16"|"fp32"   arithmetic of the fused encode+MLP kernel (default: env ONERF_PRECISION or bf16)
+  _rand=dict(...)           test hook: pre-drawn random buffers (jitter, u, noise_*), see tests/synth.py
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, Optional
+
+import torch
+
+from . import engine
+
+__all__ = ["render_rays", "sample_pdf", "inference_model"]
+
+
+def _is_voxel(embedding_xyz) -> bool:
+    return hasattr(embedding_xyz, "voxel_idx_map")
+
+
+def _grid_of(embedding_xyz):
+    return engine.GridBuffers.from_module(embedding_xyz) if _is_voxel(embedding_xyz) else None
+
+
+def _needs_grad(model, *tensors) -> bool:
+    if not torch.is_grad_enabled():
+        return False
+    return any(p.requires_grad for p in model.parameters()) or any(
+        t is not None and t.requires_grad for t in tensors)
+
+
+def sample_pdf(bins, weights, N_importance, det=False, eps=1e-5, _u=None):
+    """Reference models/rendering.py:11-61: draw N_importance depths from the piecewise-constant pdf
+    `weights` (N, M) over `bins` (N, M+1).  eps is fixed at the reference default 1e-5 in the kernel."""
+    if eps != 1e-5:
+        raise RuntimeError("sample_pdf kernel is built with eps = 1e-5")
+    seed = 0 if (det or _u is not None) else engine.new_seed()
+    return engine.sample_pdf(bins, weights, N_importance, det, u=_u, seed=seed)
+
+
+def inference_model(results: Dict[str, Any], model, embeddings: Dict[str, Any], typ: str, xyz, rays_d, z_vals,
+                    chunk: int, noise_std: float, white_back: bool, is_eval: bool = False,
+                    use_zero_as_last_delta: bool = False, forward_instance: bool = True,
+                    embedding_instance: Optional[torch.Tensor] = None, frustum_bound_th: float = 0,
+                    pass_through_mask: Optional[torch.Tensor] = None, rays_in_bbox: bool = False,
+                    precision: Optional[str] = None, _rand: Optional[dict] = None, _rays=None, _seed=None,
+                    **dummy_kwargs):
+    """Encode + two-branch MLP + compositing for one pass; fills `results` in place with the reference's
+    keys (models/rendering.py:64-230).  `chunk` is accepted and ignored: the kernels tile internally."""
+    if _needs_grad(model, embedding_instance):
+        raise NotImplementedError("backward of the fused render path is not built yet (SURVEY.md §8 row a14); "
+                                  "call under torch.no_grad()")
+    n, s = z_vals.shape
+    emb_xyz = embeddings["xyz"]
+    use_voxel = _is_voxel(emb_xyz)
+    packed = engine.packed_for(model, use_voxel)
+    grid = _grid_of(emb_xyz)
+    if _rays is None:  # explicit-xyz call surface: only the direction columns of `rays` are used
+        _rays = torch.zeros(n, 8, dtype=torch.float32, device=z_vals.device)
+        _rays[:, 3:6] = rays_d.reshape(n, 3)
+        xyz_arg = xyz
+    else:
+        xyz_arg = None
+    z = z_vals.contiguous()
+    scene, obj = engine.field(_rays, z, packed, grid, codes=embedding_instance if forward_instance else None,
+                              want_scene=True, want_object=forward_instance, precision=precision, xyz=xyz_arg)
+    rand = _rand or {}
+    seed = _seed if _seed is not None else (engine.new_seed() if noise_std > 0 else 0)
+    out = engine.composite(z, scene, obj, noise_std=noise_std, white_back=white_back, is_eval=is_eval,
+                           zero_last_delta=use_zero_as_last_delta, rays_in_bbox=rays_in_bbox,
+                           frustum_bound_th=frustum_bound_th, pass_through_mask=pass_through_mask,
+                           noise_scene=rand.get(f"noise_scene_{typ}"), noise_obj=rand.get(f"noise_obj_{typ}"),
+                           seed=seed)
+    results[f"weights_{typ}"] = out["weights"]
+    results[f"opacity_{typ}"] = out["opacity"]
+    results[f"z_vals_{typ}"] = z_vals
+    results[f"rgb_{typ}"] = out["rgb"]
+    results[f"depth_{typ}"] = out["depth"]
+    if forward_instance:
+        results[f"rgb_instance_{typ}"] = out["rgb_instance"]
+        results[f"depth_instance_{typ}"] = out["depth_instance"]
+        results[f"opacity_instance_{typ}"] = out["opacity_instance"]
+    return
+
+
+def render_rays(models: Dict[str, Any], embeddings: Dict[str, Any], rays: torch.Tensor, N_samples: int = 64,
+                use_disp: bool = False, perturb: float = 0, noise_std: float = 1, N_importance: int = 0,
+                chunk: int = 1024 * 32, white_back: bool = False, forward_instance: bool = True,
+                embedding_instance: Optional[torch.Tensor] = None, frustum_bound_th: float = 0,
+                pass_through_mask: Optional[torch.Tensor] = None, rays_in_bbox: bool = False,
+                **dummy_kwargs):
+    """Reference models/rendering.py:233-337: stratified sampling -> coarse pass -> importance resampling
+    -> fine pass.  rays (N,8) = [o, d, near, far]; returns the reference's result dict."""
+    rand = dummy_kwargs.get("_rand") or {}
+    rays = rays.contiguous().float()
+    perturb = float(perturb)
+    seed = engine.new_seed() if (perturb > 0 or noise_std > 0) else 0
+    z = engine.sample_coarse(rays, N_samples, use_disp, perturb, rand.get("jitter"), seed)
+    results: Dict[str, Any] = {}
+    common = dict(embeddings=embeddings, chunk=chunk, noise_std=noise_std, white_back=white_back,
+                  forward_instance=forward_instance, embedding_instance=embedding_instance,
+                  frustum_bound_th=frustum_bound_th, pass_through_mask=pass_through_mask,
+                  rays_in_bbox=rays_in_bbox, _rays=rays, **dummy_kwargs)
+    inference_model(results=results, model=models["coarse"], typ="coarse", xyz=None, rays_d=None, z_vals=z,
+                    _seed=seed + 1, **common)
+    if N_importance > 0:
+        z_fine = engine.sample_pdf_merge(z, results["weights_coarse"], N_importance, det=(perturb == 0),
+                                         u=rand.get("u"), seed=seed + 2)
+        inference_model(results=results, model=models["fine"], typ="fine", xyz=None, rays_d=None, z_vals=z_fine,
+                        _seed=seed + 3, **common)
+    return results
