@@ -103,7 +103,7 @@ template <bool VOXEL>
 __global__ void __launch_bounds__(256) field_fp32_kernel(FieldParams p) {
   extern __shared__ __align__(16) float smem[];
   const PackLayout& L = p.L;
-  const int KX = VOXEL ? 272 : 64, KO = VOXEL ? 384 : 64;
+  const int KX = VOXEL ? 288 : 64, KO = VOXEL ? 384 : 64;
   float* X = smem;                 // [KO][32]
   float* H0 = X + KO * TS;         // [256][32]
   float* H1 = H0 + 256 * TS;       // [256][32]

@@ -8,7 +8,7 @@
 //
 // Kernel-K order ("X layout").  The encoded input of a sample is kept as one vector X:
 //   voxel model:  X[0..271)   = scene input  [PE6(scene voxel ftr 16) | PE10(xyz)]  (reference order)
-//                 X[271]      = 0 (pad)
+//                 X[271]      = 0 (pad)   (scene GEMMs read X[0..288): their weights for 271..287 are 0)
 //                 X[272..376) = PE6(object voxel ftr 8)
 //                 X[376..384) = 0 (pad to a multiple of 32/64)
 //   plain model:  X[0..63) = PE10(xyz), X[63] = 0
@@ -44,7 +44,7 @@ struct GemmDesc {
 
 struct PackLayout {
   int use_voxel;
-  int KX, KO;       // scene / object widths of X (272/384 voxel, 64/64 plain)
+  int KX, KO;       // scene / object widths of X (288/384 voxel, 64/64 plain)
   int n_obj_vox;    // 104 or 0
   GemmDesc g[G_COUNT];
   int64_t sigma_w, sigma_b;     // [256], [1]
@@ -61,7 +61,7 @@ struct PackLayout {
 static inline PackLayout onerf_make_layout(int use_voxel) {
   PackLayout L;
   L.use_voxel = use_voxel;
-  L.KX = use_voxel ? 272 : 64;
+  L.KX = use_voxel ? 288 : 64;  // 272 rounded up to a 32-wide K slab (columns 272..287 carry zero scene weights)
   L.KO = use_voxel ? 384 : 64;
   L.n_obj_vox = use_voxel ? 104 : 0;
   const int K[G_COUNT] = {L.KX, 256, 256, 256, L.KX + 256, 256, 256, 256, 256, 256,

@@ -50,11 +50,14 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// inclusive additive warp scan
-__device__ __forceinline__ float warp_scan_add(float v, int lane) {
+// inclusive additive warp scan in double: torch's CPU cumsum accumulates fp32 rows in double and rounds
+// each prefix to fp32 (ATen cumsum_cpu_kernel, acc_type<float> = double); doing the same keeps cdf[M]
+// on the same side of 1.0 as the reference, which decides where the u = 1 sample lands when the tail
+// bins are empty (denominator guard, models/rendering.py:54-56).
+__device__ __forceinline__ double warp_scan_add(double v, int lane) {
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
-    float t = __shfl_up_sync(0xffffffffu, v, o);
+    double t = __shfl_up_sync(0xffffffffu, v, o);
     if (lane >= o) v += t;
   }
   return v;
@@ -94,13 +97,13 @@ sample_pdf_merge_kernel(const float* __restrict__ z_coarse, const float* __restr
     for (int i = lane; i < M; i += 32) part += __fadd_rn(__ldg(w + 1 + i), eps);
     const float total = warp_sum(part);
     // cdf[0] = 0, cdf[j+1] = cdf[j] + pdf_j
-    float carry = 0.0f;
+    double carry = 0.0;
     if (lane == 0) cdf[0] = 0.0f;
     for (int base = 0; base < M; base += 32) {
       const int i = base + lane;
-      float p = (i < M) ? __fdiv_rn(__fadd_rn(__ldg(w + 1 + i), eps), total) : 0.0f;
-      float s = warp_scan_add(p, lane) + carry;
-      if (i < M) cdf[i + 1] = s;
+      const float p = (i < M) ? __fdiv_rn(__fadd_rn(__ldg(w + 1 + i), eps), total) : 0.0f;
+      const double s = warp_scan_add((double)p, lane) + carry;
+      if (i < M) cdf[i + 1] = (float)s;
       carry = __shfl_sync(0xffffffffu, s, 31);
     }
     __syncwarp();
