@@ -190,14 +190,23 @@ def test_render_rays_matches_reference_golden(golden, name, precision):
     for k, v in out.items():
         assert v.is_cuda and v.dtype == torch.float32 and tuple(v.shape) == tuple(gold[k].shape), k
     close(out["z_vals_coarse"], gold["z_vals_coarse"], 1e-6, "z_vals_coarse")
+    train = c["perturb"] > 0
+    masked = (not c["is_eval"]) and c["frustum_bound_th"] > 0
     if precision == "fp32":
         # jittered fine samples can sit ~1e-4 apart, so an ulp of z is a 1e-3 relative error of that
-        # delta; with |sigma| up to ~1e2 the fp32 weights agree to a few 1e-4
+        # delta; with |sigma| up to ~1e2 the fp32 weights agree to a few 1e-4.  With random u the inverse
+        # CDF divides by pdf mass as small as 1e-5, which amplifies the same ulps in z_vals_fine.
         for k in gold:
-            close(out[k], gold[k], 5e-4 if k.startswith("weights") else 2e-4, k)
+            tol = 5e-4 if k.startswith("weights") else (1e-3 if (train and k == "z_vals_fine") else 2e-4)
+            close(out[k], gold[k], tol, k)
     else:
         for k in gold:
-            if k.startswith(("rgb", "opacity")):
+            inst = "instance" in k
+            if masked and inst:
+                # the occlusion mask (depth_scene + th < z, models/rendering.py:192-202) is a hard threshold:
+                # a bf16-sized change of the scene depth flips single samples in or out for a few rays
+                close_but(out[k], gold[k], 3e-2 if not k.startswith("depth") else 5e-2, k, 0.15, 0.6)
+            elif k.startswith(("rgb", "opacity")):
                 close(out[k], gold[k], 3e-2, k)
                 assert helpers.psnr(out[k].cpu(), gold[k]) >= 45.0, (k, helpers.psnr(out[k].cpu(), gold[k]))
             elif k.startswith("depth"):
