@@ -16,6 +16,10 @@ from . import _lib
 
 PRECISIONS = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}
 
+# bench.py's roofline pass sets this to a list; field() then brackets each field launch with CUDA events
+# on the launching stream and appends (start, end, n_rays, n_samples).  None (default) = no events.
+PROFILE_EVENTS = None
+
 
 def default_precision() -> str:
     """bf16 = tcgen05 tensor-core path (product default); fp32 = FFMA verification arithmetic."""
@@ -214,7 +218,13 @@ def field(rays, z, packed, grid: Optional[GridBuffers], codes=None, code_row=Non
     a.obj_out = obj_out.data_ptr() if want_object else None
     a.out_stride = out_stride
     a.ray_const = ray_const.data_ptr()
+    if PROFILE_EVENTS is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     _lib.check(_lib.load().onerf_field_fwd(_lib.ctx(dev), C.byref(a), _lib.stream()))
+    if PROFILE_EVENTS is not None:
+        e1.record()
+        PROFILE_EVENTS.append((e0, e1, n, s))
     return (scene_out if want_scene else None), (obj_out if want_object else None)
 
 
