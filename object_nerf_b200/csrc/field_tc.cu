@@ -2,15 +2,22 @@
 //
 // One persistent CTA per SM; a CTA owns one M = 128 tile of consecutive samples at a time.
 //   warps 0-7  (256 thr)  encode the tile into shared memory (X, bf16, UMMA K-major SWIZZLE_128B atoms) and run
-//                         every layer's epilogue: TMEM -> registers (tcgen05.ld) -> bias / per-ray constant ->
-//                         LeakyReLU -> bf16 -> shared memory (H, next layer's A operand); heads (sigma, rgb) on
-//                         CUDA cores from the fp32 accumulators.
-//   warp 8     (1 lane)   streams the weight K-slabs (N x 32 bf16, pre-swizzled SWIZZLE_64B stage images written by
-//                         pack.cu) global -> shared with cp.async.bulk (TMA) through a NSTAGE mbarrier ring.
-//   warp 9     (1 lane)   issues tcgen05.mma (M=128, N=256/128/64, K=16, bf16 x bf16 -> fp32 in TMEM) and
-//                         tcgen05.commit; also owns the TMEM allocation.
-// Skip / dir / code concatenations never materialise: a skip layer simply takes K-slabs from both X and H, and
-// the per-ray-constant terms arrive through ray_const (see layout.h).
+//                         every layer's epilogue: TMEM accumulator -> registers (tcgen05.ld) -> bias / per-ray
+//                         constant -> LeakyReLU -> bf16x2 -> back into TMEM (tcgen05.st) as the NEXT layer's A
+//                         operand.  Hidden activations never touch shared or global memory.  Heads (sigma,
+//                         rgb) are CUDA-core dot products on the fp32 values.
+//   warp 8     (1 lane)   streams the weights global -> shared with cp.async.bulk (TMA): one (N/2 x 32) bf16
+//                         half K-slab per stage (pre-swizzled SWIZZLE_64B stage images written by pack.cu),
+//                         NSTAGE-deep mbarrier ring running ahead across layers and tiles.
+//   warp 9     (1 lane)   issues tcgen05.mma (M=128, K=16, bf16 x bf16 -> fp32 in TMEM): A from shared memory
+//                         (X slabs) or from TMEM (hidden slabs), B from the weight ring; owns the TMEM allocation.
+// Overlap: every layer's N outputs are computed as two halves.  While the epilogue warps drain half 0, the tensor
+// pipe computes half 1; the next layer's half 0 starts on the K range produced by the first epilogue half as soon
+// as that is written, and waits for the second only for the remaining K slabs.
+// TMEM map (512 columns): [0,256) accumulator halves at 0 / 128, [256,384) and [384,512) activation ping-pong
+// (bf16 pairs packed in 32-bit columns: K = 2c, 2c+1 in column c).
+// Skip / dir / code concatenations never materialise: a skip layer takes K-slabs from both X and H, and the
+// per-ray-constant terms arrive through ray_const (see layout.h).
 //
 // Reference semantics: models/rendering.py:85-137, models/nerf_model.py:97-152,
 // models/embedding_helper.py:325-411, render_tools/multi_rendering.py:16-93.
@@ -23,7 +30,12 @@ namespace {
 
 constexpr int TM = 128;             // samples per tile (UMMA M)
 constexpr int NSTAGE = 3;           // weight ring depth
-constexpr int STAGE_BYTES = 16384;  // 256 rows x 64 B
+constexpr int SLAB_BYTES = 8192;    // 128 rows x 64 B: one half K-slab (32 of K) of an N = 256 layer
+constexpr int STAGE_SLABS = 4;      // a ring stage carries up to 4 consecutive K-slabs (128 of K) of one layer half
+constexpr int STAGE_BYTES = STAGE_SLABS * SLAB_BYTES;
+constexpr int MAX_GROUPS = 6;
+constexpr int TM_ACC1 = 128;        // TMEM column of accumulator half 1
+constexpr int TM_HA = 256, TM_HB = 384;
 constexpr int ATOM_BYTES = 16384;   // 128 rows x 128 B (64 bf16 of K)
 constexpr int NUM_COMPUTE = 256;
 constexpr int NUM_THREADS = 320;
@@ -39,10 +51,16 @@ struct TcLayer {
   int epi;         // Epi
   int branch;      // 0 scene, 1 object
   int rc_base;     // ray_const offset for *_RC / DIR epilogues
-  int acc_col;     // TMEM column of the accumulator
-  int pad;
+  int h_in_col;    // TMEM column of the input activations (K pairs), if nslab_h > 0
+  int h_out_col;   // TMEM column the epilogue writes the output activations to
   int64_t img_off;   // byte offset of this layer's stage images in the packed blob
   int64_t bias_off;  // float offset of the bias vector
+  // K-slab groups (one ring stage each), identical for both halves of the layer:
+  //   bits [0,5) first slab (index inside X or H), [5,8) slab count (1..4), bit 8: from H, bit 9: needs the
+  //   second epilogue half of the previous layer (high-K half of the input activations)
+  int ngroups;
+  int groups[MAX_GROUPS];
+  int pad;
 };
 
 struct TcParams {
@@ -101,6 +119,16 @@ __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint
                : "memory");
 }
 
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols) : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -116,6 +144,15 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// same with A taken from TMEM (bf16 pairs per column)
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -134,6 +171,29 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+               "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // UMMA shared-memory matrix descriptor, K-major (cute::UMMA::SmemDescriptor):
@@ -144,7 +204,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo_bytes
          ((uint64_t)1 << 46) | ((uint64_t)layout_type << 61);
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B bf16, both K-major, M = 128
-__device__ __forceinline__ uint32_t make_idesc(int N) {
+__device__ __forceinline__ uint32_t make_idesc(int N) {  // N = columns of ONE mma (a layer half)
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 }
 
@@ -216,6 +276,52 @@ __device__ __forceinline__ void pe_xyz_to_chunks(uint32_t xbase, int row, int ch
              pack_bf16(v[8 * q + 4], v[8 * q + 5]), pack_bf16(v[8 * q + 6], v[8 * q + 7]));
 }
 
+// One 16-column group of an epilogue: t = acc + bias (+ LeakyReLU), optional head partial sums, optional
+// bf16 pack -> 8 packed registers.  PER_RAY selects a global (ray_const) or shared-memory bias source.
+template <bool PER_RAY>
+__device__ __forceinline__ void epi_group16(const uint32_t* v, const float* bias, bool act, int epi,
+                                            const float* headw, int head_ld, float& p0, float& p1, float& p2,
+                                            uint32_t* packed) {
+  float t[16];
+#pragma unroll
+  for (int j4 = 0; j4 < 4; ++j4) {
+    float4 b;
+    if (PER_RAY) b = __ldg(reinterpret_cast<const float4*>(bias) + j4);
+    else b = *(reinterpret_cast<const float4*>(bias) + j4);
+    t[4 * j4 + 0] = __uint_as_float(v[4 * j4 + 0]) + b.x;
+    t[4 * j4 + 1] = __uint_as_float(v[4 * j4 + 1]) + b.y;
+    t[4 * j4 + 2] = __uint_as_float(v[4 * j4 + 2]) + b.z;
+    t[4 * j4 + 3] = __uint_as_float(v[4 * j4 + 3]) + b.w;
+  }
+  if (act) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) t[j] = fmaxf(t[j], t[j] * kLeaky);
+  }
+  if (epi == EPI_HIDDEN_SIGMA) {
+#pragma unroll
+    for (int j4 = 0; j4 < 4; ++j4) {
+      const float4 w = __ldg(reinterpret_cast<const float4*>(headw) + j4);
+      p0 = fmaf(t[4 * j4 + 0], w.x, p0); p0 = fmaf(t[4 * j4 + 1], w.y, p0);
+      p0 = fmaf(t[4 * j4 + 2], w.z, p0); p0 = fmaf(t[4 * j4 + 3], w.w, p0);
+    }
+  } else if (epi == EPI_DIR) {
+#pragma unroll
+    for (int j4 = 0; j4 < 4; ++j4) {
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(headw) + j4);
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(headw + head_ld) + j4);
+      const float4 w2 = __ldg(reinterpret_cast<const float4*>(headw + 2 * head_ld) + j4);
+      p0 = fmaf(t[4 * j4 + 0], w0.x, p0); p0 = fmaf(t[4 * j4 + 1], w0.y, p0);
+      p0 = fmaf(t[4 * j4 + 2], w0.z, p0); p0 = fmaf(t[4 * j4 + 3], w0.w, p0);
+      p1 = fmaf(t[4 * j4 + 0], w1.x, p1); p1 = fmaf(t[4 * j4 + 1], w1.y, p1);
+      p1 = fmaf(t[4 * j4 + 2], w1.z, p1); p1 = fmaf(t[4 * j4 + 3], w1.w, p1);
+      p2 = fmaf(t[4 * j4 + 0], w2.x, p2); p2 = fmaf(t[4 * j4 + 1], w2.y, p2);
+      p2 = fmaf(t[4 * j4 + 2], w2.z, p2); p2 = fmaf(t[4 * j4 + 3], w2.w, p2);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) packed[j] = pack_bf16(t[2 * j], t[2 * j + 1]);
+}
+
 template <bool VOXEL>
 __global__ void __launch_bounds__(NUM_THREADS, 1) field_tc_kernel(const __grid_constant__ TcParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -226,29 +332,40 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_tc_kernel(const __grid_c
   // ---- shared memory carve-up (base is 1024-byte aligned: required by the 128B swizzle) ----
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sX = sbase;
-  const uint32_t sH = sX + X_ATOMS * ATOM_BYTES;
-  const uint32_t sB = sH + 4 * ATOM_BYTES;
-  const uint32_t sScratch = sB + NSTAGE * STAGE_BYTES;            // [128][2][4] floats
+  const uint32_t sB = sX + X_ATOMS * ATOM_BYTES;
+  const uint32_t sBias = sB + NSTAGE * STAGE_BYTES;                 // [MAX_LAYERS][256] floats
+  const uint32_t sScratch = sBias + MAX_LAYERS * 256 * 4;           // [128][2][4] floats
   const uint32_t sBar = sScratch + TM * 2 * 4 * 4;
   const uint32_t bar_full = sBar;                                   // NSTAGE x 8 B
   const uint32_t bar_empty = sBar + 8 * NSTAGE;
-  const uint32_t bar_a_ready = sBar + 16 * NSTAGE;                  // compute -> MMA
-  const uint32_t bar_acc_ready = bar_a_ready + 8;                   // MMA -> compute
-  const uint32_t tmem_slot = bar_acc_ready + 8;
+  const uint32_t bar_x_ready = sBar + 16 * NSTAGE;                  // compute -> MMA, once per tile
+  const uint32_t bar_acc_ready = bar_x_ready + 8;                   // [2] MMA -> compute, per layer half
+  const uint32_t bar_epi_done = bar_acc_ready + 16;                 // [2] compute -> MMA, per layer half
+  const uint32_t tmem_slot = bar_epi_done + 16;
   uint8_t* gen_base = smem_raw + (sbase - smem_u32(smem_raw));
+  float* bias_tab = reinterpret_cast<float*>(gen_base + (sBias - sbase));
   float* scratch = reinterpret_cast<float*>(gen_base + (sScratch - sbase));
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - sbase));
+  const float* Pf = reinterpret_cast<const float*>(p.packed);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
     }
-    mbar_init(bar_a_ready, NUM_COMPUTE);
-    mbar_init(bar_acc_ready, 1);
+    mbar_init(bar_x_ready, NUM_COMPUTE);
+    for (int h = 0; h < 2; ++h) {
+      mbar_init(bar_acc_ready + 8 * h, 1);
+      mbar_init(bar_epi_done + 8 * h, NUM_COMPUTE);
+    }
     fence_barrier_init();
   }
   if (warp == 9) tmem_alloc(tmem_slot, 512);
+  // per-column biases of every layer -> shared memory (layers with a per-ray constant read ray_const instead)
+  for (int i = threadIdx.x; i < P.n_layers * 256; i += NUM_THREADS) {
+    const int l = i >> 8, c = i & 255;
+    bias_tab[i] = (c < P.layers[l].N) ? __ldg(Pf + P.layers[l].bias_off + c) : 0.0f;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -257,22 +374,30 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_tc_kernel(const __grid_c
   const int64_t total = (int64_t)p.n_rays * p.S;
   const int64_t n_tiles = (total + TM - 1) / TM;
   const uint8_t* blob = reinterpret_cast<const uint8_t*>(p.packed);
-  const float* Pf = reinterpret_cast<const float*>(p.packed);
 
   if (warp == 8) {
     // =============================== weight producer (TMA bulk copies) ===============================
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        for (int l = 0; l < P.n_layers; ++l) {
-          const TcLayer& Ly = P.layers[l];
-          const uint32_t bytes = (uint32_t)Ly.N * 64u;
-          const int nslab = Ly.nslab_x + Ly.nslab_h;
-          const uint8_t* src = blob + Ly.img_off;
-          for (int j = 0; j < nslab; ++j) {
+    // The whole warp runs the (uniform) loop; one elected lane talks to the barriers / TMA.
+    uint32_t stage = 0, phase = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int l = 0; l < P.n_layers; ++l) {
+        const TcLayer& Ly = P.layers[l];
+        const uint32_t slab_bytes = (uint32_t)Ly.N * 64u, half_bytes = slab_bytes >> 1;
+        const uint8_t* src = blob + Ly.img_off;
+        for (int h = 0; h < 2; ++h) {
+          for (int gi = 0; gi < Ly.ngroups; ++gi) {
+            const int grp = Ly.groups[gi];
+            const int first = grp & 31, cnt = (grp >> 5) & 7;
+            const int gslab = ((grp >> 8) & 1) ? Ly.nslab_x + first : first;   // slab index inside the layer
             mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-            mbar_expect_tx(bar_full + 8 * stage, bytes);
-            tma_bulk_g2s(sB + stage * STAGE_BYTES, src + (size_t)j * bytes, bytes, bar_full + 8 * stage);
+            if (elect_one()) {
+              mbar_expect_tx(bar_full + 8 * stage, (uint32_t)cnt * half_bytes);
+              for (int i2 = 0; i2 < cnt; ++i2)
+                tma_bulk_g2s(sB + stage * STAGE_BYTES + (uint32_t)i2 * half_bytes,
+                             src + (size_t)(gslab + i2) * slab_bytes + (size_t)h * half_bytes, half_bytes,
+                             bar_full + 8 * stage);
+            }
+            __syncwarp();
             if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
           }
         }
@@ -280,36 +405,66 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_tc_kernel(const __grid_c
     }
   } else if (warp == 9) {
     // =============================== MMA issuer ===============================
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0, a_phase = 0;
-      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        for (int l = 0; l < P.n_layers; ++l) {
-          const TcLayer& Ly = P.layers[l];
-          const uint32_t idesc = make_idesc(Ly.N);
-          const uint32_t d_tmem = tmem_base + (uint32_t)Ly.acc_col;
-          const int nslab = Ly.nslab_x + Ly.nslab_h;
-          // A operand (X at tile start, H after the previous layer's epilogue) is in shared memory, and the
-          // previous accumulator has been drained
-          mbar_wait(bar_a_ready, a_phase);
-          a_phase ^= 1;
-          tc_fence_after();
-          for (int j = 0; j < nslab; ++j) {
-            const bool from_x = j < Ly.nslab_x;
-            const int sj = from_x ? j : j - Ly.nslab_x;                  // 32-wide slab inside X or H
-            const uint32_t a_addr = (from_x ? sX : sH) + (uint32_t)(sj >> 1) * ATOM_BYTES + (uint32_t)(sj & 1) * 64u;
+    // Warp-uniform control flow (barrier waits by all lanes), tcgen05.mma / commit by one elected lane.
+    uint32_t stage = 0, phase = 0, x_phase = 0, ed_phase0 = 0, ed_phase1 = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int l = 0; l < P.n_layers; ++l) {
+        const TcLayer& Ly = P.layers[l];
+        const uint32_t idesc = make_idesc(Ly.N >> 1);
+        const uint32_t half_bytes = (uint32_t)Ly.N * 32u;
+        if (l == 0) {  // this tile's X is encoded
+          mbar_wait(bar_x_ready, x_phase);
+          x_phase ^= 1;
+        }
+        // accumulator half 0 drained and the low-K half of the input activations written (previous layer,
+        // or the previous tile's last layer)
+        mbar_wait(bar_epi_done, ed_phase0);
+        ed_phase0 ^= 1;
+        tc_fence_after();
+        bool waited1 = false;
+        for (int h = 0; h < 2; ++h) {
+          if (h == 1 && !waited1) {
+            mbar_wait(bar_epi_done + 8, ed_phase1);
+            ed_phase1 ^= 1;
+            tc_fence_after();
+            waited1 = true;
+          }
+          const uint32_t d_tmem = tmem_base + (uint32_t)(h * TM_ACC1);
+          for (int gi = 0; gi < Ly.ngroups; ++gi) {
+            const int grp = Ly.groups[gi];
+            const int first = grp & 31, cnt = (grp >> 5) & 7;
+            const bool from_h = (grp >> 8) & 1;
+            if (((grp >> 9) & 1) && !waited1) {   // high-K half of the input activations
+              mbar_wait(bar_epi_done + 8, ed_phase1);
+              ed_phase1 ^= 1;
+              tc_fence_after();
+              waited1 = true;
+            }
             mbar_wait(bar_full + 8 * stage, phase);
             tc_fence_after();
-            const uint32_t b_addr = sB + stage * STAGE_BYTES;
+            if (elect_one()) {
+              const uint32_t b_addr = sB + stage * STAGE_BYTES;
+              for (int i2 = 0; i2 < cnt; ++i2) {
+                const int sj = first + i2;
 #pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
-              const uint64_t da = make_desc(a_addr + ks * 32u, 1024u, 2u);
-              const uint64_t db = make_desc(b_addr + ks * 32u, 512u, 4u);
-              umma_bf16(d_tmem, da, db, idesc, (j > 0 || ks > 0) ? 1u : 0u);
+                for (int ks = 0; ks < 2; ++ks) {
+                  const uint64_t db = make_desc(b_addr + (uint32_t)i2 * half_bytes + ks * 32u, 512u, 4u);
+                  const uint32_t accum = (gi > 0 || i2 > 0 || ks > 0) ? 1u : 0u;
+                  if (!from_h) {
+                    const uint32_t a_addr = sX + (uint32_t)(sj >> 1) * ATOM_BYTES + (uint32_t)(sj & 1) * 64u + ks * 32u;
+                    umma_bf16(d_tmem, make_desc(a_addr, 1024u, 2u), db, idesc, accum);
+                  } else {
+                    // K = 32 sj + 16 ks .. +16  ->  8 packed columns
+                    umma_bf16_ts(d_tmem, tmem_base + (uint32_t)(Ly.h_in_col + sj * 16 + ks * 8), db, idesc, accum);
+                  }
+                }
+              }
+              umma_commit(bar_empty + 8 * stage);
+              if (gi == Ly.ngroups - 1) umma_commit(bar_acc_ready + 8 * h);
             }
-            umma_commit(bar_empty + 8 * stage);   // slab consumed -> producer may refill
+            __syncwarp();
             if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
           }
-          umma_commit(bar_acc_ready);             // accumulator complete -> epilogue
         }
       }
     }
@@ -318,7 +473,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_tc_kernel(const __grid_c
     const int q = warp & 3, hf = warp >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-    uint32_t acc_phase = 0;
+    uint32_t acc_phase0 = 0, acc_phase1 = 0;
+    // nothing to drain before the very first layer
+    mbar_arrive(bar_epi_done);
+    mbar_arrive(bar_epi_done + 8);
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int64_t e = tile * TM + row;
       const bool live = e < total;
@@ -358,77 +516,51 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_tc_kernel(const __grid_c
         if (hf == 0) pe_xyz_to_chunks(sX, row, 0, x, y, z);
       }
       fence_async_smem();
-      mbar_arrive(bar_a_ready);
+      mbar_arrive(bar_x_ready);
 
       float sigma_part = 0.0f;
       for (int l = 0; l < P.n_layers; ++l) {
         const TcLayer& Ly = P.layers[l];
-        const int ncol = Ly.N >> 1;                 // columns handled by this thread
-        const int col0 = hf * ncol;
-        mbar_wait(bar_acc_ready, acc_phase);
-        acc_phase ^= 1;
-        tc_fence_after();
+        const int Nq = Ly.N >> 2;                      // columns this thread handles per layer half (64/32/16)
         const bool to_h = Ly.epi != EPI_DIR;
         const bool act = Ly.epi != EPI_FINAL;
         const bool per_ray = (Ly.epi == EPI_HIDDEN_RC) || (Ly.epi == EPI_DIR);
-        const float* bias = per_ray ? (rc + Ly.rc_base) : (Pf + Ly.bias_off);
         const float* headw = nullptr;
         if (Ly.epi == EPI_HIDDEN_SIGMA) headw = Pf + (Ly.branch ? p.L.osigma_w : p.L.sigma_w);
         if (Ly.epi == EPI_DIR) headw = Pf + (Ly.branch ? p.L.orgb_w : p.L.rgb_w);
         float part0 = 0.0f, part1 = 0.0f, part2 = 0.0f;
-        for (int c = 0; c < ncol; c += 32) {
-          uint32_t v[32];
-          tmem_ld32(lane_taddr + (uint32_t)(Ly.acc_col + col0 + c), v);
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+          const int n0 = h * (Ly.N >> 1) + hf * Nq;    // first output column of this thread in this half
+          const uint32_t acc_addr = lane_taddr + (uint32_t)(h * TM_ACC1 + hf * Nq);
+          if (h == 0) { mbar_wait(bar_acc_ready, acc_phase0); acc_phase0 ^= 1; }
+          else { mbar_wait(bar_acc_ready + 8, acc_phase1); acc_phase1 ^= 1; }
+          tc_fence_after();
+          uint32_t v[64];
+          // issue all TMEM loads of this half first, then consume
+          tmem_ld16(acc_addr, v);
+          if (Nq >= 32) tmem_ld16(acc_addr + 16, v + 16);
+          if (Nq >= 64) { tmem_ld16(acc_addr + 32, v + 32); tmem_ld16(acc_addr + 48, v + 48); }
           tmem_ld_wait();
-          float t[32];
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(bias + col0 + c) + j4);
-            t[4 * j4 + 0] = __uint_as_float(v[4 * j4 + 0]) + b.x;
-            t[4 * j4 + 1] = __uint_as_float(v[4 * j4 + 1]) + b.y;
-            t[4 * j4 + 2] = __uint_as_float(v[4 * j4 + 2]) + b.z;
-            t[4 * j4 + 3] = __uint_as_float(v[4 * j4 + 3]) + b.w;
-          }
-          if (act) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) t[j] = fmaxf(t[j], t[j] * kLeaky);
-          }
-          if (Ly.epi == EPI_HIDDEN_SIGMA) {
-#pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 w = __ldg(reinterpret_cast<const float4*>(headw + col0 + c) + j4);
-              part0 = fmaf(t[4 * j4 + 0], w.x, part0);
-              part0 = fmaf(t[4 * j4 + 1], w.y, part0);
-              part0 = fmaf(t[4 * j4 + 2], w.z, part0);
-              part0 = fmaf(t[4 * j4 + 3], w.w, part0);
-            }
-          } else if (Ly.epi == EPI_DIR) {
-            const int hw = Ly.N;  // rgb head weights are [3][N]
-#pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 w0 = __ldg(reinterpret_cast<const float4*>(headw + col0 + c) + j4);
-              const float4 w1 = __ldg(reinterpret_cast<const float4*>(headw + hw + col0 + c) + j4);
-              const float4 w2 = __ldg(reinterpret_cast<const float4*>(headw + 2 * hw + col0 + c) + j4);
-              part0 = fmaf(t[4 * j4 + 0], w0.x, part0); part0 = fmaf(t[4 * j4 + 1], w0.y, part0);
-              part0 = fmaf(t[4 * j4 + 2], w0.z, part0); part0 = fmaf(t[4 * j4 + 3], w0.w, part0);
-              part1 = fmaf(t[4 * j4 + 0], w1.x, part1); part1 = fmaf(t[4 * j4 + 1], w1.y, part1);
-              part1 = fmaf(t[4 * j4 + 2], w1.z, part1); part1 = fmaf(t[4 * j4 + 3], w1.w, part1);
-              part2 = fmaf(t[4 * j4 + 0], w2.x, part2); part2 = fmaf(t[4 * j4 + 1], w2.y, part2);
-              part2 = fmaf(t[4 * j4 + 2], w2.z, part2); part2 = fmaf(t[4 * j4 + 3], w2.w, part2);
+          for (int g = 0; g < 4; ++g) {
+            if (g * 16 < Nq) {
+              uint32_t packed[8];
+              const int n = n0 + g * 16;
+              const float* hw = headw ? headw + n : nullptr;
+              if (per_ray) epi_group16<true>(v + 16 * g, rc + Ly.rc_base + n, act, Ly.epi, hw, Ly.N, part0, part1, part2, packed);
+              else epi_group16<false>(v + 16 * g, bias_tab + l * 256 + n, act, Ly.epi, hw, Ly.N, part0, part1, part2, packed);
+              if (to_h) tmem_st8(lane_taddr + (uint32_t)(Ly.h_out_col + (n >> 1)), packed);
             }
           }
-          if (to_h) {
-            const int chunk0 = (col0 + c) >> 3;
-#pragma unroll
-            for (int qd = 0; qd < 4; ++qd)
-              st_chunk(a_chunk_addr(sH, row, chunk0 + qd), pack_bf16(t[8 * qd + 0], t[8 * qd + 1]),
-                       pack_bf16(t[8 * qd + 2], t[8 * qd + 3]), pack_bf16(t[8 * qd + 4], t[8 * qd + 5]),
-                       pack_bf16(t[8 * qd + 6], t[8 * qd + 7]));
-          }
+          if (to_h) tmem_st_wait();
+          // accumulator half h drained, output activations of this half written
+          tc_fence_before();
+          mbar_arrive(bar_epi_done + 8 * h);
         }
         if (Ly.epi == EPI_HIDDEN_SIGMA) sigma_part = part0;
         if (Ly.epi == EPI_DIR) {
-          // combine the two column halves of this row through shared memory, finish the heads, write out
+          // combine the two column sub-ranges of this row through shared memory, finish the heads, write out
           float* sc = scratch + (row * 2 + hf) * 4;
           sc[0] = sigma_part; sc[1] = part0; sc[2] = part1; sc[3] = part2;
           asm volatile("bar.sync 1, %0;" ::"n"(NUM_COMPUTE) : "memory");
@@ -444,15 +576,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_tc_kernel(const __grid_c
             reinterpret_cast<float4*>(outp)[(int64_t)ray * p.out_stride + si] = make_float4(r, gch, b, sg);
           }
           asm volatile("bar.sync 1, %0;" ::"n"(NUM_COMPUTE) : "memory");  // scratch reusable
-        }
-        // this layer's accumulator is drained and (if any) H is written: release the MMA warp.
-        // The last layer of a tile releases the first layer of the next tile together with the X arrive.
-        if (l + 1 < P.n_layers) {
-          tc_fence_before();
-          fence_async_smem();
-          mbar_arrive(bar_a_ready);
-        } else {
-          tc_fence_before();
         }
       }
     }
@@ -473,37 +596,53 @@ int onerf_launch_field_bf16(onerf_ctx* ctx, const FieldParams& fp, cudaStream_t 
   P.f = fp;
   const int xs = L.KX / 32, xo = L.KO / 32;
   int n = 0;
-  auto add = [&](int gemm, int nx, int nh, int epi, int branch, int rc_base, int acc_col) {
-    TcLayer& t = P.layers[n++];
+  auto add = [&](int gemm, int nx, int nh, int epi, int branch, int rc_base) {
+    TcLayer& t = P.layers[n];
     t.N = L.g[gemm].N; t.nslab_x = nx; t.nslab_h = nh; t.epi = epi; t.branch = branch; t.rc_base = rc_base;
-    t.acc_col = acc_col; t.img_off = L.g[gemm].img_off; t.bias_off = L.g[gemm].bias_off;
+    t.h_in_col = (n & 1) ? TM_HB : TM_HA;     // layer n reads what layer n-1 wrote
+    t.h_out_col = (n & 1) ? TM_HA : TM_HB;
+    t.img_off = L.g[gemm].img_off; t.bias_off = L.g[gemm].bias_off;
+    // K-slab groups: X slabs in runs of 4, then the low-K and high-K halves of H in runs of 4
+    int ng = 0;
+    auto emit = [&](int first, int count, int from_h, int needs_hi) {
+      for (int o = 0; o < count; o += STAGE_SLABS) {
+        const int c = (count - o < STAGE_SLABS) ? count - o : STAGE_SLABS;
+        t.groups[ng++] = (first + o) | (c << 5) | (from_h << 8) | (needs_hi << 9);
+      }
+    };
+    emit(0, nx, 0, 0);
+    emit(0, nh / 2, 1, 0);
+    emit(nh / 2, nh - nh / 2, 1, 1);
+    t.ngroups = ng;
+    ++n;
   };
   if (fp.want_scene) {
-    add(G_S0, xs, 0, EPI_HIDDEN, 0, 0, 0);
-    add(G_S1, 0, 8, EPI_HIDDEN, 0, 0, 0);
-    add(G_S2, 0, 8, EPI_HIDDEN, 0, 0, 0);
-    add(G_S3, 0, 8, EPI_HIDDEN, 0, 0, 0);
-    add(G_S4, xs, 8, EPI_HIDDEN, 0, 0, 0);
-    add(G_S5, 0, 8, EPI_HIDDEN, 0, 0, 0);
-    add(G_S6, 0, 8, EPI_HIDDEN, 0, 0, 0);
-    add(G_S7, 0, 8, EPI_HIDDEN_SIGMA, 0, 0, 0);
-    add(G_SFIN, 0, 8, EPI_FINAL, 0, 0, 0);
-    add(G_SDIR, 0, 8, EPI_DIR, 0, RC_SDIR, 0);
+    add(G_S0, xs, 0, EPI_HIDDEN, 0, 0);
+    add(G_S1, 0, 8, EPI_HIDDEN, 0, 0);
+    add(G_S2, 0, 8, EPI_HIDDEN, 0, 0);
+    add(G_S3, 0, 8, EPI_HIDDEN, 0, 0);
+    add(G_S4, xs, 8, EPI_HIDDEN, 0, 0);
+    add(G_S5, 0, 8, EPI_HIDDEN, 0, 0);
+    add(G_S6, 0, 8, EPI_HIDDEN, 0, 0);
+    add(G_S7, 0, 8, EPI_HIDDEN_SIGMA, 0, 0);
+    add(G_SFIN, 0, 8, EPI_FINAL, 0, 0);
+    add(G_SDIR, 0, 8, EPI_DIR, 0, RC_SDIR);
   }
   if (fp.want_object) {
-    add(G_O0, xo, 0, EPI_HIDDEN_RC, 1, RC_OL0, 256);
-    add(G_O1, 0, 4, EPI_HIDDEN, 1, 0, 256);
-    add(G_O2, xo, 4, EPI_HIDDEN_RC, 1, RC_OL2, 256);
-    add(G_O3, 0, 4, EPI_HIDDEN_SIGMA, 1, 0, 256);
-    add(G_OFIN, 0, 4, EPI_FINAL, 1, 0, 256);
-    add(G_ODIR, 0, 4, EPI_DIR, 1, RC_ODIR, 256);
+    add(G_O0, xo, 0, EPI_HIDDEN_RC, 1, RC_OL0);
+    add(G_O1, 0, 4, EPI_HIDDEN, 1, 0);
+    add(G_O2, xo, 4, EPI_HIDDEN_RC, 1, RC_OL2);
+    add(G_O3, 0, 4, EPI_HIDDEN_SIGMA, 1, 0);
+    add(G_OFIN, 0, 4, EPI_FINAL, 1, 0);
+    add(G_ODIR, 0, 4, EPI_DIR, 1, RC_ODIR);
   }
   P.n_layers = n;
   P.x_atoms = L.use_voxel ? 6 : 1;
   const int64_t total = (int64_t)fp.n_rays * fp.S;
   const int64_t tiles = (total + TM - 1) / TM;
   const int blocks = (int)(tiles < ctx->num_sms ? tiles : ctx->num_sms);
-  const size_t smem = 1024 + (size_t)(P.x_atoms + 4) * ATOM_BYTES + NSTAGE * STAGE_BYTES + TM * 2 * 4 * 4 + 256;
+  const size_t smem = 1024 + (size_t)P.x_atoms * ATOM_BYTES + NSTAGE * STAGE_BYTES + MAX_LAYERS * 256 * 4 +
+                      TM * 2 * 4 * 4 + 512;
   if (L.use_voxel) {
     ONERF_CUDA(cudaFuncSetAttribute(field_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     field_tc_kernel<true><<<blocks, NUM_THREADS, smem, stream>>>(P);
