@@ -1,15 +1,15 @@
 // tcgen05 (5th-gen tensor core) implementation of the fused encode + two-branch MLP for sm_100a.
 //
 // One persistent CTA per SM; a CTA owns one M = 128 tile of consecutive samples at a time.
-//   warps 0-7  (256 thr)  encode the tile into shared memory (X, bf16, UMMA K-major SWIZZLE_128B atoms) and run
+//   warps 0-15 (512 thr)  encode the tile into shared memory (X, bf16, UMMA K-major SWIZZLE_128B atoms) and run
 //                         every layer's epilogue: TMEM accumulator -> registers (tcgen05.ld) -> bias / per-ray
 //                         constant -> LeakyReLU -> bf16x2 -> back into TMEM (tcgen05.st) as the NEXT layer's A
 //                         operand.  Hidden activations never touch shared or global memory.  Heads (sigma,
 //                         rgb) are CUDA-core dot products on the fp32 values.
-//   warp 8     (1 lane)   streams the weights global -> shared with cp.async.bulk (TMA): one (N/2 x 32) bf16
+//   warp 16    (1 lane)   streams the weights global -> shared with cp.async.bulk (TMA): one (N/2 x 32) bf16
 //                         half K-slab per stage (pre-swizzled SWIZZLE_64B stage images written by pack.cu),
 //                         NSTAGE-deep mbarrier ring running ahead across layers and tiles.
-//   warp 9     (1 lane)   issues tcgen05.mma (M=128, K=16, bf16 x bf16 -> fp32 in TMEM): A from shared memory
+//   warp 17    (1 lane)   issues tcgen05.mma (M=128, K=16, bf16 x bf16 -> fp32 in TMEM): A from shared memory
 //                         (X slabs) or from TMEM (hidden slabs), B from the weight ring; owns the TMEM allocation.
 // Overlap: every layer's N outputs are computed as two halves.  While the epilogue warps drain half 0, the tensor
 // pipe computes half 1; the next layer's half 0 starts on the K range produced by the first epilogue half as soon
@@ -37,8 +37,9 @@ constexpr int MAX_GROUPS = 6;
 constexpr int TM_ACC1 = 128;        // TMEM column of accumulator half 1
 constexpr int TM_HA = 256, TM_HB = 384;
 constexpr int ATOM_BYTES = 16384;   // 128 rows x 128 B (64 bf16 of K)
-constexpr int NUM_COMPUTE = 256;
-constexpr int NUM_THREADS = 320;
+constexpr int NUM_COMPUTE = 512;    // 16 encode/epilogue warps: 4 per TMEM lane quarter
+constexpr int PRODUCER_WARP = 16, MMA_WARP = 17;
+constexpr int NUM_THREADS = 576;
 constexpr int MAX_LAYERS = 16;
 constexpr float kLeaky = 0.01f;
 
@@ -227,7 +228,7 @@ __device__ __forceinline__ void pe8_to_chunks(uint32_t xbase, int row, int chunk
   st_chunk(a_chunk_addr(xbase, row, chunk0), pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]),
            pack_bf16(f[6], f[7]));
 #pragma unroll
-  for (int j = 0; j < 8; ++j) sincosf(f[j], &s[j], &c[j]);
+  for (int j = 0; j < 8; ++j) __sincosf(f[j], &s[j], &c[j]);  // |f| = O(1), 6 octaves: error stays << bf16 ulp
 #pragma unroll
   for (int k = 0; k < 6; ++k) {
     st_chunk(a_chunk_addr(xbase, row, chunk0 + stride * (1 + 2 * k)), pack_bf16(s[0], s[1]), pack_bf16(s[2], s[3]),
@@ -245,81 +246,156 @@ __device__ __forceinline__ void pe8_to_chunks(uint32_t xbase, int row, int chunk
   }
 }
 
-// PE10(xyz): 63 values in reference order + one zero -> 8 chunks starting at chunk0
+// PE10(xyz): 63 values in reference order + one zero -> 8 chunks starting at chunk0.  Values are packed to
+// bf16 pairs as they are produced (the stream position is a compile-time constant after unrolling).
 __device__ __forceinline__ void pe_xyz_to_chunks(uint32_t xbase, int row, int chunk0, float x, float y, float z) {
-  float v[64];
-  v[0] = x; v[1] = y; v[2] = z;
+  uint32_t pk[32];
+  float pend = 0.0f;
+  int pos = 0;
+  auto emit = [&](float val) {
+    if ((pos & 1) == 0) pend = val;
+    else pk[pos >> 1] = pack_bf16(pend, val);
+    ++pos;
+  };
+  emit(x); emit(y); emit(z);
   float s[3], c[3];
   sincosf(x, &s[0], &c[0]);
   sincosf(y, &s[1], &c[1]);
   sincosf(z, &s[2], &c[2]);
 #pragma unroll
   for (int k = 0; k < 10; ++k) {
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      v[3 * (1 + 2 * k) + j] = s[j];
-      v[3 * (2 + 2 * k) + j] = c[j];
-    }
+    emit(s[0]); emit(s[1]); emit(s[2]);
+    emit(c[0]); emit(c[1]); emit(c[2]);
     if (k < 9) {
 #pragma unroll
-      for (int j = 0; j < 3; ++j) {
+      for (int j = 0; j < 3; ++j) {  // double-angle step to the next octave
         const float s2 = 2.0f * s[j] * c[j];
         c[j] = fmaf(-2.0f * s[j], s[j], 1.0f);
         s[j] = s2;
       }
     }
   }
-  v[63] = 0.0f;
+  emit(0.0f);
 #pragma unroll
   for (int q = 0; q < 8; ++q)
-    st_chunk(a_chunk_addr(xbase, row, chunk0 + q), pack_bf16(v[8 * q], v[8 * q + 1]), pack_bf16(v[8 * q + 2], v[8 * q + 3]),
-             pack_bf16(v[8 * q + 4], v[8 * q + 5]), pack_bf16(v[8 * q + 6], v[8 * q + 7]));
+    st_chunk(a_chunk_addr(xbase, row, chunk0 + q), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
 }
 
-// One 16-column group of an epilogue: t = acc + bias (+ LeakyReLU), optional head partial sums, optional
-// bf16 pack -> 8 packed registers.  PER_RAY selects a global (ray_const) or shared-memory bias source.
-template <bool PER_RAY>
-__device__ __forceinline__ void epi_group16(const uint32_t* v, const float* bias, bool act, int epi,
-                                            const float* headw, int head_ld, float& p0, float& p1, float& p2,
-                                            uint32_t* packed) {
-  float t[16];
+// ------------------------------------------------------------------------------------------------
+// epilogue of one layer half for one thread: NC accumulator columns of its row
+// ------------------------------------------------------------------------------------------------
+template <int NC>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t* v) {
+  if constexpr (NC == 32) { tmem_ld16(taddr, v); tmem_ld16(taddr + 16, v + 16); }
+  else if constexpr (NC == 16) { tmem_ld16(taddr, v); }
+  else {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
+  }
+}
+template <int NP>
+__device__ __forceinline__ void tmem_st_cols(uint32_t taddr, const uint32_t* v) {
+  if constexpr (NP == 16) tmem_st16(taddr, v);
+  else if constexpr (NP == 8) tmem_st8(taddr, v);
+  else asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(v[0]), "r"(v[1]),
+                    "r"(v[2]), "r"(v[3]) : "memory");
+}
+
+__device__ __forceinline__ uint32_t leaky_bf16x2(uint32_t x) {
+  __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&x);
+  const __nv_bfloat162 slope = __floats2bfloat162_rn(kLeaky, kLeaky);
+  v = __hmax2(v, __hmul2(v, slope));
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// Hidden / final layer: t = acc + bias in fp32, one rounding to bf16, LeakyReLU on packed bf16 pairs,
+// result written to TMEM as the next layer's A operand.  BIAS_GLOBAL: per-ray constant from global memory.
+template <int NC, bool ACT, bool BIAS_GLOBAL>
+__device__ __forceinline__ void epi_hidden(uint32_t acc_addr, const float* bias, uint32_t out_addr) {
+  uint32_t v[NC];
+  tmem_ld_cols<NC>(acc_addr, v);
+  tmem_ld_wait();
+  uint32_t pk[NC / 2];
 #pragma unroll
-  for (int j4 = 0; j4 < 4; ++j4) {
+  for (int j4 = 0; j4 < NC / 4; ++j4) {
     float4 b;
-    if (PER_RAY) b = __ldg(reinterpret_cast<const float4*>(bias) + j4);
+    if (BIAS_GLOBAL) b = __ldg(reinterpret_cast<const float4*>(bias) + j4);
     else b = *(reinterpret_cast<const float4*>(bias) + j4);
-    t[4 * j4 + 0] = __uint_as_float(v[4 * j4 + 0]) + b.x;
-    t[4 * j4 + 1] = __uint_as_float(v[4 * j4 + 1]) + b.y;
-    t[4 * j4 + 2] = __uint_as_float(v[4 * j4 + 2]) + b.z;
-    t[4 * j4 + 3] = __uint_as_float(v[4 * j4 + 3]) + b.w;
+    uint32_t p0 = pack_bf16(__uint_as_float(v[4 * j4 + 0]) + b.x, __uint_as_float(v[4 * j4 + 1]) + b.y);
+    uint32_t p1 = pack_bf16(__uint_as_float(v[4 * j4 + 2]) + b.z, __uint_as_float(v[4 * j4 + 3]) + b.w);
+    if (ACT) { p0 = leaky_bf16x2(p0); p1 = leaky_bf16x2(p1); }
+    pk[2 * j4] = p0;
+    pk[2 * j4 + 1] = p1;
   }
-  if (act) {
+  tmem_st_cols<NC / 2>(out_addr, pk);
+  tmem_st_wait();
+}
+
+// Last hidden layer of a branch: like epi_hidden, plus the sigma head as an fp32 dot product on the
+// un-rounded activations (reference: sigma = Linear(h), models/nerf_model.py:108,140).
+template <int NC>
+__device__ __forceinline__ float epi_hidden_sigma(uint32_t acc_addr, const float* bias, const float* headw, uint32_t out_addr) {
+  uint32_t v[NC];
+  tmem_ld_cols<NC>(acc_addr, v);
+  tmem_ld_wait();
+  uint32_t pk[NC / 2];
+  float part = 0.0f;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) t[j] = fmaxf(t[j], t[j] * kLeaky);
+  for (int j4 = 0; j4 < NC / 4; ++j4) {
+    const float4 b = *(reinterpret_cast<const float4*>(bias) + j4);
+    const float4 w = __ldg(reinterpret_cast<const float4*>(headw) + j4);
+    float t0 = __uint_as_float(v[4 * j4 + 0]) + b.x, t1 = __uint_as_float(v[4 * j4 + 1]) + b.y;
+    float t2 = __uint_as_float(v[4 * j4 + 2]) + b.z, t3 = __uint_as_float(v[4 * j4 + 3]) + b.w;
+    t0 = fmaxf(t0, t0 * kLeaky); t1 = fmaxf(t1, t1 * kLeaky); t2 = fmaxf(t2, t2 * kLeaky); t3 = fmaxf(t3, t3 * kLeaky);
+    part = fmaf(t0, w.x, part); part = fmaf(t1, w.y, part); part = fmaf(t2, w.z, part); part = fmaf(t3, w.w, part);
+    pk[2 * j4] = pack_bf16(t0, t1);
+    pk[2 * j4 + 1] = pack_bf16(t2, t3);
   }
-  if (epi == EPI_HIDDEN_SIGMA) {
+  tmem_st_cols<NC / 2>(out_addr, pk);
+  tmem_st_wait();
+  return part;
+}
+
+// Direction layer: LeakyReLU(acc + per-ray constant) feeds the 3-wide rgb head directly (fp32 dots).
+template <int NC>
+__device__ __forceinline__ void epi_dir(uint32_t acc_addr, const float* rcbias, const float* headw, int head_ld,
+                                        float& p0, float& p1, float& p2) {
+  uint32_t v[NC];
+  tmem_ld_cols<NC>(acc_addr, v);
+  tmem_ld_wait();
 #pragma unroll
-    for (int j4 = 0; j4 < 4; ++j4) {
-      const float4 w = __ldg(reinterpret_cast<const float4*>(headw) + j4);
-      p0 = fmaf(t[4 * j4 + 0], w.x, p0); p0 = fmaf(t[4 * j4 + 1], w.y, p0);
-      p0 = fmaf(t[4 * j4 + 2], w.z, p0); p0 = fmaf(t[4 * j4 + 3], w.w, p0);
+  for (int j4 = 0; j4 < NC / 4; ++j4) {
+    const float4 b = __ldg(reinterpret_cast<const float4*>(rcbias) + j4);
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(headw) + j4);
+    const float4 w1 = __ldg(reinterpret_cast<const float4*>(headw + head_ld) + j4);
+    const float4 w2 = __ldg(reinterpret_cast<const float4*>(headw + 2 * head_ld) + j4);
+    float t0 = __uint_as_float(v[4 * j4 + 0]) + b.x, t1 = __uint_as_float(v[4 * j4 + 1]) + b.y;
+    float t2 = __uint_as_float(v[4 * j4 + 2]) + b.z, t3 = __uint_as_float(v[4 * j4 + 3]) + b.w;
+    t0 = fmaxf(t0, t0 * kLeaky); t1 = fmaxf(t1, t1 * kLeaky); t2 = fmaxf(t2, t2 * kLeaky); t3 = fmaxf(t3, t3 * kLeaky);
+    p0 = fmaf(t0, w0.x, p0); p0 = fmaf(t1, w0.y, p0); p0 = fmaf(t2, w0.z, p0); p0 = fmaf(t3, w0.w, p0);
+    p1 = fmaf(t0, w1.x, p1); p1 = fmaf(t1, w1.y, p1); p1 = fmaf(t2, w1.z, p1); p1 = fmaf(t3, w1.w, p1);
+    p2 = fmaf(t0, w2.x, p2); p2 = fmaf(t1, w2.y, p2); p2 = fmaf(t2, w2.z, p2); p2 = fmaf(t3, w2.w, p2);
+  }
+}
+
+// dispatch on the (warp-uniform) layer width; NC = N / 8 columns per thread per layer half
+template <int NC>
+__device__ __forceinline__ void epilogue_half(const TcLayer& Ly, uint32_t acc_addr, uint32_t out_addr, const float* bias_smem,
+                                              const float* rc, const float* headw, int n, float& part0, float& part1,
+                                              float& part2) {
+  if constexpr (NC >= 16) {
+    switch (Ly.epi) {
+      case EPI_HIDDEN: epi_hidden<NC, true, false>(acc_addr, bias_smem + n, out_addr); break;
+      case EPI_HIDDEN_RC: epi_hidden<NC, true, true>(acc_addr, rc + Ly.rc_base + n, out_addr); break;
+      case EPI_FINAL: epi_hidden<NC, false, false>(acc_addr, bias_smem + n, out_addr); break;
+      case EPI_HIDDEN_SIGMA: part0 += epi_hidden_sigma<NC>(acc_addr, bias_smem + n, headw + n, out_addr); break;
+      default: epi_dir<NC>(acc_addr, rc + Ly.rc_base + n, headw + n, Ly.N, part0, part1, part2); break;
     }
-  } else if (epi == EPI_DIR) {
-#pragma unroll
-    for (int j4 = 0; j4 < 4; ++j4) {
-      const float4 w0 = __ldg(reinterpret_cast<const float4*>(headw) + j4);
-      const float4 w1 = __ldg(reinterpret_cast<const float4*>(headw + head_ld) + j4);
-      const float4 w2 = __ldg(reinterpret_cast<const float4*>(headw + 2 * head_ld) + j4);
-      p0 = fmaf(t[4 * j4 + 0], w0.x, p0); p0 = fmaf(t[4 * j4 + 1], w0.y, p0);
-      p0 = fmaf(t[4 * j4 + 2], w0.z, p0); p0 = fmaf(t[4 * j4 + 3], w0.w, p0);
-      p1 = fmaf(t[4 * j4 + 0], w1.x, p1); p1 = fmaf(t[4 * j4 + 1], w1.y, p1);
-      p1 = fmaf(t[4 * j4 + 2], w1.z, p1); p1 = fmaf(t[4 * j4 + 3], w1.w, p1);
-      p2 = fmaf(t[4 * j4 + 0], w2.x, p2); p2 = fmaf(t[4 * j4 + 1], w2.y, p2);
-      p2 = fmaf(t[4 * j4 + 2], w2.z, p2); p2 = fmaf(t[4 * j4 + 3], w2.w, p2);
-    }
+  } else {
+    epi_dir<NC>(acc_addr, rc + Ly.rc_base + n, headw + n, Ly.N, part0, part1, part2);  // only the N = 64 dir layer
   }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) packed[j] = pack_bf16(t[2 * j], t[2 * j + 1]);
 }
 
 template <bool VOXEL>
@@ -334,8 +410,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_tc_kernel(const __grid_c
   const uint32_t sX = sbase;
   const uint32_t sB = sX + X_ATOMS * ATOM_BYTES;
   const uint32_t sBias = sB + NSTAGE * STAGE_BYTES;                 // [MAX_LAYERS][256] floats
-  const uint32_t sScratch = sBias + MAX_LAYERS * 256 * 4;           // [128][2][4] floats
-  const uint32_t sBar = sScratch + TM * 2 * 4 * 4;
+  const uint32_t sScratch = sBias + MAX_LAYERS * 256 * 4;           // [128][4][4] floats
+  const uint32_t sBar = sScratch + TM * 4 * 4 * 4;
   const uint32_t bar_full = sBar;                                   // NSTAGE x 8 B
   const uint32_t bar_empty = sBar + 8 * NSTAGE;
   const uint32_t bar_x_ready = sBar + 16 * NSTAGE;                  // compute -> MMA, once per tile
@@ -360,7 +436,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_tc_kernel(const __grid_c
     }
     fence_barrier_init();
   }
-  if (warp == 9) tmem_alloc(tmem_slot, 512);
+  if (warp == MMA_WARP) tmem_alloc(tmem_slot, 512);
   // per-column biases of every layer -> shared memory (layers with a per-ray constant read ray_const instead)
   for (int i = threadIdx.x; i < P.n_layers * 256; i += NUM_THREADS) {
     const int l = i >> 8, c = i & 255;
@@ -375,7 +451,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_tc_kernel(const __grid_c
   const int64_t n_tiles = (total + TM - 1) / TM;
   const uint8_t* blob = reinterpret_cast<const uint8_t*>(p.packed);
 
-  if (warp == 8) {
+  if (warp == PRODUCER_WARP) {
     // =============================== weight producer (TMA bulk copies) ===============================
     // The whole warp runs the (uniform) loop; one elected lane talks to the barriers / TMA.
     uint32_t stage = 0, phase = 0;
@@ -403,7 +479,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_tc_kernel(const __grid_c
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == MMA_WARP) {
     // =============================== MMA issuer ===============================
     // Warp-uniform control flow (barrier waits by all lanes), tcgen05.mma / commit by one elected lane.
     uint32_t stage = 0, phase = 0, x_phase = 0, ed_phase0 = 0, ed_phase1 = 0;
@@ -470,7 +546,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_tc_kernel(const __grid_c
     }
   } else {
     // =============================== encode + epilogue warps ===============================
-    const int q = warp & 3, hf = warp >> 2;
+    const int q = warp & 3, cq = warp >> 2;          // TMEM lane quarter (rows), column quarter
     const int row = q * 32 + lane;
     const uint32_t lane_taddr = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t acc_phase0 = 0, acc_phase1 = 0;
@@ -493,27 +569,31 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_tc_kernel(const __grid_c
       }
       if (!live) { x = 0.f; y = 0.f; z = 0.f; }
       int mute = 0;  // bit 0: scene sigma muted, bit 1: object sigma muted
-      if (live && p.mute_zero_rays && __ldg(p.z + (int64_t)ray * p.z_stride + (p.S - 1)) == 0.0f) mute = 3;
-      if (live && mute == 0 && p.n_boxes > 0 && point_in_boxes(p.boxes, p.n_boxes, x, y, z)) mute = 1;
+      if (cq == 0) {
+        if (live && p.mute_zero_rays && __ldg(p.z + (int64_t)ray * p.z_stride + (p.S - 1)) == 0.0f) mute = 3;
+        if (live && mute == 0 && p.n_boxes > 0 && point_in_boxes(p.boxes, p.n_boxes, x, y, z)) mute = 1;
+      }
       const float* rc = p.ray_const + (int64_t)ray * ONERF_RAY_CONST_FLOATS;
 
-      // ---- encode this row's half of X ----
+      // ---- encode this thread's quarter of the row of X ----
       if (VOXEL) {
         const GridView g = load_grid_view(p.grid);
-        if (hf == 0) {
-          float f[16];
-          voxel_trilinear<0, 16, false>(g, x, y, z, f);
-          pe8_to_chunks(sX, row, 0, 2, f);        // channels 0-7 : chunks 0, 2, 4, ...
-          pe8_to_chunks(sX, row, 1, 2, f + 8);    // channels 8-15: chunks 1, 3, 5, ...
-        } else {
-          float f[8];
+        float f[8];
+        if (cq == 0) {
+          voxel_trilinear<0, 8, false>(g, x, y, z, f);
+          pe8_to_chunks(sX, row, 0, 2, f);        // scene channels 0-7 : chunks 0, 2, 4, ...
+        } else if (cq == 1) {
+          voxel_trilinear<8, 8, false>(g, x, y, z, f);
+          pe8_to_chunks(sX, row, 1, 2, f);        // scene channels 8-15: chunks 1, 3, 5, ...
+        } else if (cq == 2) {
           voxel_trilinear<16, 8, false>(g, x, y, z, f);
           pe8_to_chunks(sX, row, 34, 1, f);       // object voxel block starts at column 272 = chunk 34
+        } else {
           pe_xyz_to_chunks(sX, row, 26, x, y, z); // columns 208..271
           st_chunk(a_chunk_addr(sX, row, 47), 0u, 0u, 0u, 0u);  // columns 376..383
         }
       } else {
-        if (hf == 0) pe_xyz_to_chunks(sX, row, 0, x, y, z);
+        if (cq == 0) pe_xyz_to_chunks(sX, row, 0, x, y, z);
       }
       fence_async_smem();
       mbar_arrive(bar_x_ready);
@@ -521,56 +601,41 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_tc_kernel(const __grid_c
       float sigma_part = 0.0f;
       for (int l = 0; l < P.n_layers; ++l) {
         const TcLayer& Ly = P.layers[l];
-        const int Nq = Ly.N >> 2;                      // columns this thread handles per layer half (64/32/16)
-        const bool to_h = Ly.epi != EPI_DIR;
-        const bool act = Ly.epi != EPI_FINAL;
-        const bool per_ray = (Ly.epi == EPI_HIDDEN_RC) || (Ly.epi == EPI_DIR);
+        const int NC = Ly.N >> 3;                      // columns this thread handles per layer half (32/16/8)
         const float* headw = nullptr;
         if (Ly.epi == EPI_HIDDEN_SIGMA) headw = Pf + (Ly.branch ? p.L.osigma_w : p.L.sigma_w);
         if (Ly.epi == EPI_DIR) headw = Pf + (Ly.branch ? p.L.orgb_w : p.L.rgb_w);
         float part0 = 0.0f, part1 = 0.0f, part2 = 0.0f;
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
-          const int n0 = h * (Ly.N >> 1) + hf * Nq;    // first output column of this thread in this half
-          const uint32_t acc_addr = lane_taddr + (uint32_t)(h * TM_ACC1 + hf * Nq);
+          const int n = h * (Ly.N >> 1) + cq * NC;     // first output column of this thread in this half
+          const uint32_t acc_addr = lane_taddr + (uint32_t)(h * TM_ACC1 + cq * NC);
+          const uint32_t out_addr = lane_taddr + (uint32_t)(Ly.h_out_col + (n >> 1));
           if (h == 0) { mbar_wait(bar_acc_ready, acc_phase0); acc_phase0 ^= 1; }
           else { mbar_wait(bar_acc_ready + 8, acc_phase1); acc_phase1 ^= 1; }
           tc_fence_after();
-          uint32_t v[64];
-          // issue all TMEM loads of this half first, then consume
-          tmem_ld16(acc_addr, v);
-          if (Nq >= 32) tmem_ld16(acc_addr + 16, v + 16);
-          if (Nq >= 64) { tmem_ld16(acc_addr + 32, v + 32); tmem_ld16(acc_addr + 48, v + 48); }
-          tmem_ld_wait();
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            if (g * 16 < Nq) {
-              uint32_t packed[8];
-              const int n = n0 + g * 16;
-              const float* hw = headw ? headw + n : nullptr;
-              if (per_ray) epi_group16<true>(v + 16 * g, rc + Ly.rc_base + n, act, Ly.epi, hw, Ly.N, part0, part1, part2, packed);
-              else epi_group16<false>(v + 16 * g, bias_tab + l * 256 + n, act, Ly.epi, hw, Ly.N, part0, part1, part2, packed);
-              if (to_h) tmem_st8(lane_taddr + (uint32_t)(Ly.h_out_col + (n >> 1)), packed);
-            }
-          }
-          if (to_h) tmem_st_wait();
+          if (NC == 32) epilogue_half<32>(Ly, acc_addr, out_addr, bias_tab + l * 256, rc, headw, n, part0, part1, part2);
+          else if (NC == 16) epilogue_half<16>(Ly, acc_addr, out_addr, bias_tab + l * 256, rc, headw, n, part0, part1, part2);
+          else epilogue_half<8>(Ly, acc_addr, out_addr, bias_tab + l * 256, rc, headw, n, part0, part1, part2);
           // accumulator half h drained, output activations of this half written
           tc_fence_before();
           mbar_arrive(bar_epi_done + 8 * h);
         }
         if (Ly.epi == EPI_HIDDEN_SIGMA) sigma_part = part0;
         if (Ly.epi == EPI_DIR) {
-          // combine the two column sub-ranges of this row through shared memory, finish the heads, write out
-          float* sc = scratch + (row * 2 + hf) * 4;
+          // combine the four column quarters of this row through shared memory, finish the heads, write out
+          float* sc = scratch + (row * 4 + cq) * 4;
           sc[0] = sigma_part; sc[1] = part0; sc[2] = part1; sc[3] = part2;
           asm volatile("bar.sync 1, %0;" ::"n"(NUM_COMPUTE) : "memory");
-          if (hf == 0 && live) {
-            const float* o = scratch + (row * 2 + 1) * 4;
+          if (cq == 0 && live) {
+            const float4 a1 = *reinterpret_cast<const float4*>(scratch + (row * 4 + 1) * 4);
+            const float4 a2 = *reinterpret_cast<const float4*>(scratch + (row * 4 + 2) * 4);
+            const float4 a3 = *reinterpret_cast<const float4*>(scratch + (row * 4 + 3) * 4);
             const float* hb = Pf + (Ly.branch ? p.L.orgb_b : p.L.rgb_b);
-            float sg = sigma_part + o[0] + __ldg(Pf + (Ly.branch ? p.L.osigma_b : p.L.sigma_b));
-            const float r = 1.0f / (1.0f + __expf(-(part0 + o[1] + __ldg(hb + 0))));
-            const float gch = 1.0f / (1.0f + __expf(-(part1 + o[2] + __ldg(hb + 1))));
-            const float b = 1.0f / (1.0f + __expf(-(part2 + o[3] + __ldg(hb + 2))));
+            float sg = sigma_part + a1.x + a2.x + a3.x + __ldg(Pf + (Ly.branch ? p.L.osigma_b : p.L.sigma_b));
+            const float r = 1.0f / (1.0f + __expf(-(part0 + a1.y + a2.y + a3.y + __ldg(hb + 0))));
+            const float gch = 1.0f / (1.0f + __expf(-(part1 + a1.z + a2.z + a3.z + __ldg(hb + 1))));
+            const float b = 1.0f / (1.0f + __expf(-(part2 + a1.w + a2.w + a3.w + __ldg(hb + 2))));
             if (mute & (Ly.branch ? 2 : 1)) sg = -1e5f;
             float* outp = Ly.branch ? p.obj_out : p.scene_out;
             reinterpret_cast<float4*>(outp)[(int64_t)ray * p.out_stride + si] = make_float4(r, gch, b, sg);
@@ -584,7 +649,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_tc_kernel(const __grid_c
   // ---- teardown ----
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) tmem_dealloc(tmem_base, 512);
+  if (warp == MMA_WARP) tmem_dealloc(tmem_base, 512);
 }
 
 }  // namespace
@@ -642,7 +707,7 @@ int onerf_launch_field_bf16(onerf_ctx* ctx, const FieldParams& fp, cudaStream_t 
   const int64_t tiles = (total + TM - 1) / TM;
   const int blocks = (int)(tiles < ctx->num_sms ? tiles : ctx->num_sms);
   const size_t smem = 1024 + (size_t)P.x_atoms * ATOM_BYTES + NSTAGE * STAGE_BYTES + MAX_LAYERS * 256 * 4 +
-                      TM * 2 * 4 * 4 + 512;
+                      TM * 4 * 4 * 4 + 512;
   if (L.use_voxel) {
     ONERF_CUDA(cudaFuncSetAttribute(field_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     field_tc_kernel<true><<<blocks, NUM_THREADS, smem, stream>>>(P);
