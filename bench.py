@@ -107,13 +107,15 @@ def run_reference(args, rank, world):
         return
     from oracle import onerf_oracle as O
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     sc = build_scene("cpu")
     g = sc["grid"]
     grid = O.VoxelGrid(g["offset"], g["voxel_size"], g["shape"].tolist(), g["idx_map"], g["table"])
-    n = 4096
+    n = 2048
     sel = torch.linspace(0, N_RAYS - 1, n).long()
     rays, codes = sc["rays"][sel], sc["codes"][sel]
+    with torch.no_grad():
+        threads = pick_cpu_threads(lambda: O.render_rays(sc["weights"], grid, rays[:256], codes[:256], n_samples=N_SAMPLES,
+                                                         n_importance=N_IMPORTANCE, is_eval=True))
 
     def step():
         with torch.no_grad():
@@ -127,21 +129,41 @@ def run_reference(args, rank, world):
         step()
     dt = time.perf_counter() - t0
     val = n * args.steps / dt
-    sample = f"{n} rays of the frame (every {N_RAYS // n}th) per step, torch CPU fp32, {cores} threads"
+    sample = (f"{n} rays of the frame (every {N_RAYS // n}th) per step, oracle port (torch CPU fp32), {threads} torch "
+              f"threads (fastest of a probe; host has {cores} logical cores)")
     print(json.dumps({
         "impl": "reference", "metric": "rays/s", "value": val, "unit": "rays/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "rays_per_step": n},
-        "cpu_baseline": {"value": val, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "rays/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+def pick_cpu_threads(fn):
+    """torch's CPU matmuls on these small (32768 x 256) chunks get slower when oversubscribed (128 threads on
+    the B200 host: 101 rays/s vs 468 rays/s at 16, profiles/r01_cpu_threads.md), so "all the host threads it
+    can use" is found by timing a small probe at a few thread counts and keeping the fastest."""
+    cores = os.cpu_count() or 1
+    best, best_t = cores, None
+    for t in sorted({cores, max(1, cores // 2), max(1, cores // 4), 32, 16}, reverse=True):
+        if t > cores:
+            continue
+        torch.set_num_threads(t)
+        fn()
+        t0 = time.perf_counter()
+        fn()
+        dt = time.perf_counter() - t0
+        if best_t is None or dt < best_t:
+            best, best_t = t, dt
+    torch.set_num_threads(best)
+    return best
 
 
 def cpu_baseline_sample():
     from oracle import onerf_oracle as O
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     sc = build_scene("cpu")
     g = sc["grid"]
     grid = O.VoxelGrid(g["offset"], g["voxel_size"], g["shape"].tolist(), g["idx_map"], g["table"])
@@ -149,15 +171,17 @@ def cpu_baseline_sample():
     sel = torch.linspace(0, N_RAYS - 1, n).long()
     rays, codes = sc["rays"][sel], sc["codes"][sel]
     with torch.no_grad():
-        O.render_rays(sc["weights"], grid, rays[:512], codes[:512], n_samples=N_SAMPLES, n_importance=N_IMPORTANCE, is_eval=True)
+        threads = pick_cpu_threads(lambda: O.render_rays(sc["weights"], grid, rays[:256], codes[:256], n_samples=N_SAMPLES,
+                                                         n_importance=N_IMPORTANCE, is_eval=True))
         t0 = time.perf_counter()
         reps = 0
         while reps < 2 or (time.perf_counter() - t0 < 10.0 and reps < 8):
             O.render_rays(sc["weights"], grid, rays, codes, n_samples=N_SAMPLES, n_importance=N_IMPORTANCE, is_eval=True)
             reps += 1
         dt = time.perf_counter() - t0
-    return {"value": n * reps / dt, "unit": "rays/s", "cores": cores, "kind": "port",
-            "sample": f"{reps} x {n} rays of the frame, oracle port (torch CPU fp32), {cores} threads"}
+    return {"value": n * reps / dt, "unit": "rays/s", "cores": threads, "kind": "port",
+            "sample": f"{reps} x {n} rays of the frame, oracle port (torch CPU fp32), {threads} torch threads "
+                      f"(fastest of a probe over thread counts; host has {cores} logical cores)"}
 
 
 def run_ours(args, rank, world, local_rank):
@@ -252,7 +276,7 @@ def run_ours(args, rank, world, local_rank):
         return
     value = N_RAYS * world * args.steps / (ms * 1e-3)
     e2e = N_RAYS * world * args.steps / (ms_e2e * 1e-3)
-    cpu = cpu_baseline_sample() if world == 1 else None
+    cpu = cpu_baseline_sample() if (world == 1 and not args.no_cpu) else None
     line = {
         "metric": "rays/s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -285,6 +309,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (development runs)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -429,10 +429,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_tc_kernel(const __grid_c
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
     }
-    mbar_init(bar_x_ready, NUM_COMPUTE);
+    // compute -> MMA barriers take ONE arrive per warp (after __syncwarp): 512 serialized shared-memory
+    // atomics per phase would cost more than the epilogue math
+    mbar_init(bar_x_ready, NUM_COMPUTE / 32);
     for (int h = 0; h < 2; ++h) {
       mbar_init(bar_acc_ready + 8 * h, 1);
-      mbar_init(bar_epi_done + 8 * h, NUM_COMPUTE);
+      mbar_init(bar_epi_done + 8 * h, NUM_COMPUTE / 32);
     }
     fence_barrier_init();
   }
@@ -551,8 +553,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_tc_kernel(const __grid_c
     const uint32_t lane_taddr = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t acc_phase0 = 0, acc_phase1 = 0;
     // nothing to drain before the very first layer
-    mbar_arrive(bar_epi_done);
-    mbar_arrive(bar_epi_done + 8);
+    if (lane == 0) {
+      mbar_arrive(bar_epi_done);
+      mbar_arrive(bar_epi_done + 8);
+    }
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int64_t e = tile * TM + row;
       const bool live = e < total;
@@ -596,7 +600,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_tc_kernel(const __grid_c
         if (cq == 0) pe_xyz_to_chunks(sX, row, 0, x, y, z);
       }
       fence_async_smem();
-      mbar_arrive(bar_x_ready);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_x_ready);
 
       float sigma_part = 0.0f;
       for (int l = 0; l < P.n_layers; ++l) {
@@ -619,7 +624,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_tc_kernel(const __grid_c
           else epilogue_half<8>(Ly, acc_addr, out_addr, bias_tab + l * 256, rc, headw, n, part0, part1, part2);
           // accumulator half h drained, output activations of this half written
           tc_fence_before();
-          mbar_arrive(bar_epi_done + 8 * h);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_epi_done + 8 * h);
         }
         if (Ly.epi == EPI_HIDDEN_SIGMA) sigma_part = part0;
         if (Ly.epi == EPI_DIR) {
