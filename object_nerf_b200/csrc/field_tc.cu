@@ -204,6 +204,14 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo_bytes
   return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
          ((uint64_t)1 << 46) | ((uint64_t)layout_type << 61);
 }
+// same, from a precomputed high word and a low word ((addr >> 4) & 0x3FFF) | (1 << 16)
+constexpr uint32_t DESC_HI_SW128 = (1024u >> 4) | (1u << 14) | (2u << 29);
+constexpr uint32_t DESC_HI_SW64 = (512u >> 4) | (1u << 14) | (4u << 29);
+__device__ __forceinline__ uint64_t make_desc_hl(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
 // instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B bf16, both K-major, M = 128
 __device__ __forceinline__ uint32_t make_idesc(int N) {  // N = columns of ONE mma (a layer half)
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
@@ -521,19 +529,32 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_tc_kernel(const __grid_c
             mbar_wait(bar_full + 8 * stage, phase);
             tc_fence_after();
             if (elect_one()) {
-              const uint32_t b_addr = sB + stage * STAGE_BYTES;
-              for (int i2 = 0; i2 < cnt; ++i2) {
-                const int sj = first + i2;
+              // Descriptors: the high words are constants, the low words advance by (bytes >> 4) per K step.
+              const uint32_t b_lo0 = (((sB + stage * STAGE_BYTES) >> 4) & 0x3FFFu) | 0x10000u;
+              const uint32_t hb16 = half_bytes >> 4;
+              uint32_t accum = (gi > 0) ? 1u : 0u;
+              if (!from_h) {
+                // X slabs: `first` is a multiple of 4, i.e. atom aligned; slab i2 sits at atom (i2 >> 1), half (i2 & 1)
+                const uint32_t a_lo0 = (((sX + (uint32_t)(first >> 1) * ATOM_BYTES) >> 4) & 0x3FFFu) | 0x10000u;
 #pragma unroll
-                for (int ks = 0; ks < 2; ++ks) {
-                  const uint64_t db = make_desc(b_addr + (uint32_t)i2 * half_bytes + ks * 32u, 512u, 4u);
-                  const uint32_t accum = (gi > 0 || i2 > 0 || ks > 0) ? 1u : 0u;
-                  if (!from_h) {
-                    const uint32_t a_addr = sX + (uint32_t)(sj >> 1) * ATOM_BYTES + (uint32_t)(sj & 1) * 64u + ks * 32u;
-                    umma_bf16(d_tmem, make_desc(a_addr, 1024u, 2u), db, idesc, accum);
-                  } else {
-                    // K = 32 sj + 16 ks .. +16  ->  8 packed columns
-                    umma_bf16_ts(d_tmem, tmem_base + (uint32_t)(Ly.h_in_col + sj * 16 + ks * 8), db, idesc, accum);
+                for (int i2 = 0; i2 < STAGE_SLABS; ++i2) {
+                  if (i2 < cnt) {
+                    const uint32_t a_lo = a_lo0 + (uint32_t)(i2 >> 1) * (ATOM_BYTES >> 4) + (uint32_t)(i2 & 1) * 4u;
+                    const uint32_t b_lo = b_lo0 + (uint32_t)i2 * hb16;
+                    umma_bf16(d_tmem, make_desc_hl(a_lo, DESC_HI_SW128), make_desc_hl(b_lo, DESC_HI_SW64), idesc, accum);
+                    umma_bf16(d_tmem, make_desc_hl(a_lo + 2u, DESC_HI_SW128), make_desc_hl(b_lo + 2u, DESC_HI_SW64), idesc, 1u);
+                    accum = 1u;
+                  }
+                }
+              } else {
+                const uint32_t a_t0 = tmem_base + (uint32_t)(Ly.h_in_col + first * 16);
+#pragma unroll
+                for (int i2 = 0; i2 < STAGE_SLABS; ++i2) {
+                  if (i2 < cnt) {
+                    const uint32_t b_lo = b_lo0 + (uint32_t)i2 * hb16;
+                    umma_bf16_ts(d_tmem, a_t0 + (uint32_t)i2 * 16u, make_desc_hl(b_lo, DESC_HI_SW64), idesc, accum);
+                    umma_bf16_ts(d_tmem, a_t0 + (uint32_t)i2 * 16u + 8u, make_desc_hl(b_lo + 2u, DESC_HI_SW64), idesc, 1u);
+                    accum = 1u;
                   }
                 }
               }
