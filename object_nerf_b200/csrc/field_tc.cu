@@ -66,6 +66,7 @@ struct TcLayer {
 
 struct TcParams {
   FieldParams f;
+  long long* timeline;   // debug: per-event clock64() of block 0, second tile (null = off); see tools/timeline.py
   TcLayer layers[MAX_LAYERS];
   int n_layers;
   int x_atoms;     // 6 (voxel) or 1 (plain)
@@ -516,6 +517,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_tc_kernel(const __grid_c
             waited1 = true;
           }
           const uint32_t d_tmem = tmem_base + (uint32_t)(h * TM_ACC1);
+          if (P.timeline && blockIdx.x == 0 && tile == (int64_t)gridDim.x && lane == 0) P.timeline[(l * 2 + h) * 4 + 0] = clock64();
           for (int gi = 0; gi < Ly.ngroups; ++gi) {
             const int grp = Ly.groups[gi];
             const int first = grp & 31, cnt = (grp >> 5) & 7;
@@ -561,6 +563,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_tc_kernel(const __grid_c
               umma_commit(bar_empty + 8 * stage);
               if (gi == Ly.ngroups - 1) umma_commit(bar_acc_ready + 8 * h);
             }
+            if (gi == Ly.ngroups - 1 && P.timeline && blockIdx.x == 0 && tile == (int64_t)gridDim.x && lane == 0)
+              P.timeline[(l * 2 + h) * 4 + 1] = clock64();
             __syncwarp();
             if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
           }
@@ -579,6 +583,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_tc_kernel(const __grid_c
       mbar_arrive(bar_epi_done + 8);
     }
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      if (P.timeline && blockIdx.x == 0 && tile == (int64_t)gridDim.x && threadIdx.x == 0) P.timeline[201] = clock64();
       const int64_t e = tile * TM + row;
       const bool live = e < total;
       const int ray = live ? (int)(e / p.S) : 0;
@@ -623,6 +628,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_tc_kernel(const __grid_c
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_x_ready);
+      if (P.timeline && blockIdx.x == 0 && tile == (int64_t)gridDim.x && threadIdx.x == 0) P.timeline[200] = clock64();
 
       float sigma_part = 0.0f;
       for (int l = 0; l < P.n_layers; ++l) {
@@ -640,6 +646,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_tc_kernel(const __grid_c
           if (h == 0) { mbar_wait(bar_acc_ready, acc_phase0); acc_phase0 ^= 1; }
           else { mbar_wait(bar_acc_ready + 8, acc_phase1); acc_phase1 ^= 1; }
           tc_fence_after();
+          if (P.timeline && blockIdx.x == 0 && tile == (int64_t)gridDim.x && threadIdx.x == 0) P.timeline[(l * 2 + h) * 4 + 2] = clock64();
           if (NC == 32) epilogue_half<32>(Ly, acc_addr, out_addr, bias_tab + l * 256, rc, headw, n, part0, part1, part2);
           else if (NC == 16) epilogue_half<16>(Ly, acc_addr, out_addr, bias_tab + l * 256, rc, headw, n, part0, part1, part2);
           else epilogue_half<8>(Ly, acc_addr, out_addr, bias_tab + l * 256, rc, headw, n, part0, part1, part2);
@@ -647,6 +654,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_tc_kernel(const __grid_c
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_epi_done + 8 * h);
+          if (P.timeline && blockIdx.x == 0 && tile == (int64_t)gridDim.x && threadIdx.x == 0) P.timeline[(l * 2 + h) * 4 + 3] = clock64();
         }
         if (Ly.epi == EPI_HIDDEN_SIGMA) sigma_part = part0;
         if (Ly.epi == EPI_DIR) {
@@ -681,11 +689,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_tc_kernel(const __grid_c
 
 }  // namespace
 
+static long long* g_timeline = nullptr;
+extern "C" void onerf_debug_timeline(void* dev_buf) { g_timeline = reinterpret_cast<long long*>(dev_buf); }
+
 int onerf_launch_field_bf16(onerf_ctx* ctx, const FieldParams& fp, cudaStream_t stream) {
   const PackLayout& L = fp.L;
   TcParams P;
   memset(&P, 0, sizeof(P));
   P.f = fp;
+  P.timeline = g_timeline;
   const int xs = L.KX / 32, xo = L.KO / 32;
   int n = 0;
   auto add = [&](int gemm, int nx, int nh, int epi, int branch, int rc_base) {

@@ -187,8 +187,21 @@ def gen_multi_cases():
         save("multi_" + name, **out)
 
 
+def gen_gridbuild():
+    """Cold path pin: the reference's EmbeddingVoxel constructor on a synthetic cloud (ScanNet-0113-like
+    voxel_size / scale_factor / scene_center, config/scannet_base_0113_multi.yml:7-11,43-44)."""
+    pts = np.random.default_rng(0).uniform([0, 0, -1], [4, 4, 1], size=(20000, 3))
+    R.register_pointcloud("synthetic", pts)
+    extra = R.AttrDict(pcd_path="synthetic", scene_center=[2.0, 2.0, 0.0], scale_factor=2.0, voxel_size=0.1,
+                       neighbor_marks=3)
+    emb = EmbeddingVoxel(24, 6, 50000, extra)
+    save("gridbuild", voxel_shape=emb.voxel_shape, voxel_idx_map=emb.voxel_idx_map, voxel_offset=emb.voxel_offset,
+         voxel_size=emb.voxel_size)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    gen_gridbuild()
     gen_stage_cases()
     gen_render_cases()
     gen_multi_cases()
