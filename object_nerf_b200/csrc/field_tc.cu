@@ -64,8 +64,25 @@ struct TcLayer {
   int pad;
 };
 
+// One weight-ring stage of the flattened per-tile program (built on the host, copied to shared memory):
+// up to STAGE_SLABS consecutive K-slabs of one layer half.
+struct StageDesc {
+  uint32_t a_off;       // A operand: from X: offset from sX in 16-byte units; from H: TMEM column of the first slab
+  uint32_t src_off;     // byte offset in the packed blob of the first half-slab image
+  uint32_t slab_bytes;  // distance between consecutive slabs in the blob (N * 64)
+  uint16_t hb16;        // bytes >> 4 of one half-slab (N/2 * 64 >> 4): 512 / 256 / 128
+  uint8_t cnt;          // slabs in this stage (1..4)
+  uint8_t flags;        // ST_* bits
+};
+enum : uint8_t {
+  ST_FROM_H = 1, ST_FIRST = 2, ST_WAIT_X = 4, ST_WAIT_E0 = 8, ST_WAIT_E1 = 16, ST_COMMIT_ACC = 32, ST_HALF1 = 64
+};
+constexpr int MAX_STAGES = 112;
+
 struct TcParams {
   FieldParams f;
+  StageDesc stages[MAX_STAGES];
+  int n_stages;
   long long* timeline;   // debug: per-event clock64() of block 0, second tile (null = off); see tools/timeline.py
   TcLayer layers[MAX_LAYERS];
   int n_layers;
@@ -91,6 +108,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {   // non-blocking probe
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
       : "r"(bar), "r"(parity)
@@ -156,6 +184,25 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
       "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
       "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// accumulate flag as a compile-time constant (folds to UPT / !UPT: no register -> predicate round trip)
+template <bool ACC>
+__device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc) {
+  if constexpr (ACC)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 1;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+                 "l"(desc_a), "l"(desc_b), "r"(idesc) : "memory");
+  else
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, 1, 1;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+                 "l"(desc_a), "l"(desc_b), "r"(idesc) : "memory");
+}
+template <bool ACC>
+__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc) {
+  if constexpr (ACC)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 1;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+                 "r"(tmem_a), "l"(desc_b), "r"(idesc) : "memory");
+  else
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, 1, 1;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+                 "r"(tmem_a), "l"(desc_b), "r"(idesc) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -407,6 +454,56 @@ __device__ __forceinline__ void epilogue_half(const TcLayer& Ly, uint32_t acc_ad
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// MMA issue of one ring stage: CNT K-slabs (2 K-steps each) as straight-line code with immediate offsets.
+//   FROM_H: A from TMEM (a0 = TMEM address of the first slab's packed K columns), else A from shared memory
+//           (a0 = descriptor low word of the first slab; X groups start atom-aligned)
+//   HB16:   bytes >> 4 of one half K-slab in the ring stage (N/2 rows x 64 B)
+// ------------------------------------------------------------------------------------------------
+template <bool FROM_H, int CNT, int HB16, bool FIRST>
+__device__ __forceinline__ void issue_stage(uint32_t d_tmem, uint32_t a0, uint32_t b_lo0, uint32_t idesc) {
+#pragma unroll
+  for (int i2 = 0; i2 < CNT; ++i2) {
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      const uint64_t db = make_desc_hl(b_lo0 + (uint32_t)(i2 * HB16 + ks * 2), DESC_HI_SW64);
+      if constexpr (FROM_H) {
+        const uint32_t ta = a0 + (uint32_t)(i2 * 16 + ks * 8);
+        if (FIRST && i2 == 0 && ks == 0) umma_ts<false>(d_tmem, ta, db, idesc);
+        else umma_ts<true>(d_tmem, ta, db, idesc);
+      } else {
+        const uint64_t da = make_desc_hl(a0 + (uint32_t)((i2 >> 1) * (ATOM_BYTES >> 4) + (i2 & 1) * 4 + ks * 2), DESC_HI_SW128);
+        if (FIRST && i2 == 0 && ks == 0) umma_ss<false>(d_tmem, da, db, idesc);
+        else umma_ss<true>(d_tmem, da, db, idesc);
+      }
+    }
+  }
+}
+template <bool FROM_H, int HB16>
+__device__ __forceinline__ void issue_stage_cnt(int cnt, bool first, uint32_t d_tmem, uint32_t a0, uint32_t b_lo0, uint32_t idesc) {
+  if (first) {
+    switch (cnt) {
+      case 4: issue_stage<FROM_H, 4, HB16, true>(d_tmem, a0, b_lo0, idesc); break;
+      case 3: issue_stage<FROM_H, 3, HB16, true>(d_tmem, a0, b_lo0, idesc); break;
+      case 2: issue_stage<FROM_H, 2, HB16, true>(d_tmem, a0, b_lo0, idesc); break;
+      default: issue_stage<FROM_H, 1, HB16, true>(d_tmem, a0, b_lo0, idesc); break;
+    }
+  } else {
+    switch (cnt) {
+      case 4: issue_stage<FROM_H, 4, HB16, false>(d_tmem, a0, b_lo0, idesc); break;
+      case 3: issue_stage<FROM_H, 3, HB16, false>(d_tmem, a0, b_lo0, idesc); break;
+      case 2: issue_stage<FROM_H, 2, HB16, false>(d_tmem, a0, b_lo0, idesc); break;
+      default: issue_stage<FROM_H, 1, HB16, false>(d_tmem, a0, b_lo0, idesc); break;
+    }
+  }
+}
+template <bool FROM_H>
+__device__ __forceinline__ void issue_stage_n(int N, int cnt, bool first, uint32_t d_tmem, uint32_t a0, uint32_t b_lo0, uint32_t idesc) {
+  if (N == 256) issue_stage_cnt<FROM_H, 512>(cnt, first, d_tmem, a0, b_lo0, idesc);
+  else if (N == 128) issue_stage_cnt<FROM_H, 256>(cnt, first, d_tmem, a0, b_lo0, idesc);
+  else issue_stage_cnt<FROM_H, 128>(cnt, first, d_tmem, a0, b_lo0, idesc);
+}
+
 template <bool VOXEL>
 __global__ void __launch_bounds__(NUM_THREADS, 1) field_tc_kernel(const __grid_constant__ TcParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -420,7 +517,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_tc_kernel(const __grid_c
   const uint32_t sB = sX + X_ATOMS * ATOM_BYTES;
   const uint32_t sBias = sB + NSTAGE * STAGE_BYTES;                 // [MAX_LAYERS][256] floats
   const uint32_t sScratch = sBias + MAX_LAYERS * 256 * 4;           // [128][4][4] floats
-  const uint32_t sBar = sScratch + TM * 4 * 4 * 4;
+  const uint32_t sStages = sScratch + TM * 4 * 4 * 4;               // [MAX_STAGES] StageDesc
+  const uint32_t sBar = sStages + MAX_STAGES * 16;
   const uint32_t bar_full = sBar;                                   // NSTAGE x 8 B
   const uint32_t bar_empty = sBar + 8 * NSTAGE;
   const uint32_t bar_x_ready = sBar + 16 * NSTAGE;                  // compute -> MMA, once per tile
@@ -430,6 +528,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_tc_kernel(const __grid_c
   uint8_t* gen_base = smem_raw + (sbase - smem_u32(smem_raw));
   float* bias_tab = reinterpret_cast<float*>(gen_base + (sBias - sbase));
   float* scratch = reinterpret_cast<float*>(gen_base + (sScratch - sbase));
+  uint4* stage_tab = reinterpret_cast<uint4*>(gen_base + (sStages - sbase));
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - sbase));
   const float* Pf = reinterpret_cast<const float*>(p.packed);
 
@@ -453,6 +552,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_tc_kernel(const __grid_c
     const int l = i >> 8, c = i & 255;
     bias_tab[i] = (c < P.layers[l].N) ? __ldg(Pf + P.layers[l].bias_off + c) : 0.0f;
   }
+  for (int i = threadIdx.x; i < P.n_stages; i += NUM_THREADS)
+    stage_tab[i] = *reinterpret_cast<const uint4*>(&P.stages[i]);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -464,111 +565,65 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_tc_kernel(const __grid_c
 
   if (warp == PRODUCER_WARP) {
     // =============================== weight producer (TMA bulk copies) ===============================
-    // The whole warp runs the (uniform) loop; one elected lane talks to the barriers / TMA.
+    // The whole warp runs the (uniform) loop over the flattened stage program; one elected lane talks to the
+    // barriers / TMA.  It runs ahead of the MMA warp by the ring depth, across layers and tiles.
     uint32_t stage = 0, phase = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      for (int l = 0; l < P.n_layers; ++l) {
-        const TcLayer& Ly = P.layers[l];
-        const uint32_t slab_bytes = (uint32_t)Ly.N * 64u, half_bytes = slab_bytes >> 1;
-        const uint8_t* src = blob + Ly.img_off;
-        for (int h = 0; h < 2; ++h) {
-          for (int gi = 0; gi < Ly.ngroups; ++gi) {
-            const int grp = Ly.groups[gi];
-            const int first = grp & 31, cnt = (grp >> 5) & 7;
-            const int gslab = ((grp >> 8) & 1) ? Ly.nslab_x + first : first;   // slab index inside the layer
-            mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-            if (elect_one()) {
-              mbar_expect_tx(bar_full + 8 * stage, (uint32_t)cnt * half_bytes);
-              for (int i2 = 0; i2 < cnt; ++i2)
-                tma_bulk_g2s(sB + stage * STAGE_BYTES + (uint32_t)i2 * half_bytes,
-                             src + (size_t)(gslab + i2) * slab_bytes + (size_t)h * half_bytes, half_bytes,
-                             bar_full + 8 * stage);
-            }
-            __syncwarp();
-            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
-          }
+      for (int si = 0; si < P.n_stages; ++si) {
+        const uint4 raw = stage_tab[si];
+        const uint32_t half_bytes = (raw.w & 0xFFFFu) << 4, cnt = (raw.w >> 16) & 0xFFu;
+        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(bar_full + 8 * stage, cnt * half_bytes);
+          const uint8_t* src = blob + raw.y;
+          for (uint32_t i2 = 0; i2 < cnt; ++i2)
+            tma_bulk_g2s(sB + stage * STAGE_BYTES + i2 * half_bytes, src + (size_t)i2 * raw.z, half_bytes,
+                         bar_full + 8 * stage);
         }
+        __syncwarp();
+        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == MMA_WARP) {
     // =============================== MMA issuer ===============================
-    // Warp-uniform control flow (barrier waits by all lanes), tcgen05.mma / commit by one elected lane.
+    // Warp-uniform loop over the flattened stage program.  The next stage's descriptor is fetched and its
+    // `full` barrier probed BEFORE the current stage's MMAs are issued, so neither latency sits between two
+    // bursts of tcgen05.mma.  Barrier waits are executed by all lanes, mma / commit by one elected lane.
     uint32_t stage = 0, phase = 0, x_phase = 0, ed_phase0 = 0, ed_phase1 = 0;
+    int tl_idx = 0;
+    uint4 cur = stage_tab[0];
+    bool cur_ready = false;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      for (int l = 0; l < P.n_layers; ++l) {
-        const TcLayer& Ly = P.layers[l];
-        const uint32_t idesc = make_idesc(Ly.N >> 1);
-        const uint32_t half_bytes = (uint32_t)Ly.N * 32u;
-        if (l == 0) {  // this tile's X is encoded
-          mbar_wait(bar_x_ready, x_phase);
-          x_phase ^= 1;
-        }
-        // accumulator half 0 drained and the low-K half of the input activations written (previous layer,
-        // or the previous tile's last layer)
-        mbar_wait(bar_epi_done, ed_phase0);
-        ed_phase0 ^= 1;
+      for (int si = 0; si < P.n_stages; ++si) {
+        const uint32_t flags = cur.w >> 24, cnt = (cur.w >> 16) & 0xFFu, hb16 = cur.w & 0xFFFFu;
+        const bool tl = P.timeline && blockIdx.x == 0 && tile == (int64_t)gridDim.x && lane == 0;
+        if (tl) P.timeline[256 + (tl_idx * 3 + 0)] = clock64();
+        if (flags & ST_WAIT_X) { mbar_wait(bar_x_ready, x_phase); x_phase ^= 1; }
+        if (flags & ST_WAIT_E0) { mbar_wait(bar_epi_done, ed_phase0); ed_phase0 ^= 1; }
+        if (flags & ST_WAIT_E1) { mbar_wait(bar_epi_done + 8, ed_phase1); ed_phase1 ^= 1; }
+        if (!cur_ready) mbar_wait(bar_full + 8 * stage, phase);
         tc_fence_after();
-        bool waited1 = false;
-        for (int h = 0; h < 2; ++h) {
-          if (h == 1 && !waited1) {
-            mbar_wait(bar_epi_done + 8, ed_phase1);
-            ed_phase1 ^= 1;
-            tc_fence_after();
-            waited1 = true;
-          }
-          const uint32_t d_tmem = tmem_base + (uint32_t)(h * TM_ACC1);
-          if (P.timeline && blockIdx.x == 0 && tile == (int64_t)gridDim.x && lane == 0) P.timeline[(l * 2 + h) * 4 + 0] = clock64();
-          for (int gi = 0; gi < Ly.ngroups; ++gi) {
-            const int grp = Ly.groups[gi];
-            const int first = grp & 31, cnt = (grp >> 5) & 7;
-            const bool from_h = (grp >> 8) & 1;
-            if (((grp >> 9) & 1) && !waited1) {   // high-K half of the input activations
-              mbar_wait(bar_epi_done + 8, ed_phase1);
-              ed_phase1 ^= 1;
-              tc_fence_after();
-              waited1 = true;
-            }
-            mbar_wait(bar_full + 8 * stage, phase);
-            tc_fence_after();
-            if (elect_one()) {
-              // Descriptors: the high words are constants, the low words advance by (bytes >> 4) per K step.
-              const uint32_t b_lo0 = (((sB + stage * STAGE_BYTES) >> 4) & 0x3FFFu) | 0x10000u;
-              const uint32_t hb16 = half_bytes >> 4;
-              uint32_t accum = (gi > 0) ? 1u : 0u;
-              if (!from_h) {
-                // X slabs: `first` is a multiple of 4, i.e. atom aligned; slab i2 sits at atom (i2 >> 1), half (i2 & 1)
-                const uint32_t a_lo0 = (((sX + (uint32_t)(first >> 1) * ATOM_BYTES) >> 4) & 0x3FFFu) | 0x10000u;
-#pragma unroll
-                for (int i2 = 0; i2 < STAGE_SLABS; ++i2) {
-                  if (i2 < cnt) {
-                    const uint32_t a_lo = a_lo0 + (uint32_t)(i2 >> 1) * (ATOM_BYTES >> 4) + (uint32_t)(i2 & 1) * 4u;
-                    const uint32_t b_lo = b_lo0 + (uint32_t)i2 * hb16;
-                    umma_bf16(d_tmem, make_desc_hl(a_lo, DESC_HI_SW128), make_desc_hl(b_lo, DESC_HI_SW64), idesc, accum);
-                    umma_bf16(d_tmem, make_desc_hl(a_lo + 2u, DESC_HI_SW128), make_desc_hl(b_lo + 2u, DESC_HI_SW64), idesc, 1u);
-                    accum = 1u;
-                  }
-                }
-              } else {
-                const uint32_t a_t0 = tmem_base + (uint32_t)(Ly.h_in_col + first * 16);
-#pragma unroll
-                for (int i2 = 0; i2 < STAGE_SLABS; ++i2) {
-                  if (i2 < cnt) {
-                    const uint32_t b_lo = b_lo0 + (uint32_t)i2 * hb16;
-                    umma_bf16_ts(d_tmem, a_t0 + (uint32_t)i2 * 16u, make_desc_hl(b_lo, DESC_HI_SW64), idesc, accum);
-                    umma_bf16_ts(d_tmem, a_t0 + (uint32_t)i2 * 16u + 8u, make_desc_hl(b_lo + 2u, DESC_HI_SW64), idesc, 1u);
-                    accum = 1u;
-                  }
-                }
-              }
-              umma_commit(bar_empty + 8 * stage);
-              if (gi == Ly.ngroups - 1) umma_commit(bar_acc_ready + 8 * h);
-            }
-            if (gi == Ly.ngroups - 1 && P.timeline && blockIdx.x == 0 && tile == (int64_t)gridDim.x && lane == 0)
-              P.timeline[(l * 2 + h) * 4 + 1] = clock64();
-            __syncwarp();
-            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
-          }
+        if (tl) P.timeline[256 + (tl_idx * 3 + 1)] = clock64();
+        // prefetch the next stage's descriptor and probe its barrier (the stage table wraps around per tile)
+        const int sn = (si + 1 == P.n_stages) ? 0 : si + 1;
+        const uint4 nxt = stage_tab[sn];
+        const uint32_t nstage = (stage + 1 == NSTAGE) ? 0u : stage + 1, nphase = (stage + 1 == NSTAGE) ? phase ^ 1u : phase;
+        const bool nxt_ready = mbar_test_wait(bar_full + 8 * nstage, nphase);
+        if (elect_one()) {
+          const uint32_t d_tmem = tmem_base + ((flags & ST_HALF1) ? (uint32_t)TM_ACC1 : 0u);
+          const uint32_t b_lo0 = (((sB + stage * STAGE_BYTES) >> 4) & 0x3FFFu) | 0x10000u;
+          const int N = (int)(hb16 >> 1);
+          const uint32_t idesc = make_idesc(N >> 1);
+          const bool first = (flags & ST_FIRST) != 0;
+          if (flags & ST_FROM_H) issue_stage_n<true>(N, (int)cnt, first, d_tmem, tmem_base + cur.x, b_lo0, idesc);
+          else issue_stage_n<false>(N, (int)cnt, first, d_tmem, ((((sX >> 4) + cur.x)) & 0x3FFFu) | 0x10000u, b_lo0, idesc);
+          umma_commit(bar_empty + 8 * stage);
+          if (flags & ST_COMMIT_ACC) umma_commit(bar_acc_ready + ((flags & ST_HALF1) ? 8u : 0u));
         }
+        __syncwarp();
+        if (tl) { P.timeline[256 + (tl_idx * 3 + 2)] = clock64(); ++tl_idx; }
+        stage = nstage; phase = nphase;
+        cur = nxt; cur_ready = nxt_ready;
       }
     }
   } else {
@@ -742,11 +797,42 @@ int onerf_launch_field_bf16(onerf_ctx* ctx, const FieldParams& fp, cudaStream_t 
   }
   P.n_layers = n;
   P.x_atoms = L.use_voxel ? 6 : 1;
+  // flatten: for each layer, for each half, one stage per K-slab group
+  int ns = 0;
+  for (int l = 0; l < n; ++l) {
+    const TcLayer& t = P.layers[l];
+    const uint32_t slab_bytes = (uint32_t)t.N * 64u, half_bytes = slab_bytes / 2;
+    bool waited1 = false;   // per layer: the second epilogue half of the previous layer is waited for once
+    for (int h = 0; h < 2; ++h) {
+      for (int gi = 0; gi < t.ngroups; ++gi) {
+        const int grp = t.groups[gi];
+        const int first = grp & 31, cnt = (grp >> 5) & 7, from_h = (grp >> 8) & 1, needs_hi = (grp >> 9) & 1;
+        if (ns >= MAX_STAGES) { onerf_set_error("field_tc: stage program too long"); return ONERF_ERR_UNSUPPORTED; }
+        StageDesc& sd = P.stages[ns++];
+        uint8_t fl = 0;
+        if (from_h) fl |= ST_FROM_H;
+        if (gi == 0) fl |= ST_FIRST;
+        if (h == 1) fl |= ST_HALF1;
+        if (l == 0 && h == 0 && gi == 0) fl |= ST_WAIT_X;
+        if (h == 0 && gi == 0) fl |= ST_WAIT_E0;               // accumulator half 0 drained, low-K activations written
+        if (!waited1 && (h == 1 || needs_hi)) { fl |= ST_WAIT_E1; waited1 = true; }   // half 1 drained / high-K written
+        if (gi == t.ngroups - 1) fl |= ST_COMMIT_ACC;
+        sd.flags = fl;
+        sd.cnt = (uint8_t)cnt;
+        sd.hb16 = (uint16_t)(half_bytes >> 4);
+        sd.slab_bytes = slab_bytes;
+        const int gslab = from_h ? t.nslab_x + first : first;
+        sd.src_off = (uint32_t)(t.img_off + (int64_t)gslab * slab_bytes + (int64_t)h * half_bytes);
+        sd.a_off = from_h ? (uint32_t)(t.h_in_col + first * 16) : (uint32_t)((first >> 1) * (ATOM_BYTES >> 4));
+      }
+    }
+  }
+  P.n_stages = ns;
   const int64_t total = (int64_t)fp.n_rays * fp.S;
   const int64_t tiles = (total + TM - 1) / TM;
   const int blocks = (int)(tiles < ctx->num_sms ? tiles : ctx->num_sms);
   const size_t smem = 1024 + (size_t)P.x_atoms * ATOM_BYTES + NSTAGE * STAGE_BYTES + MAX_LAYERS * 256 * 4 +
-                      TM * 4 * 4 * 4 + 512;
+                      TM * 4 * 4 * 4 + MAX_STAGES * 16 + 512;
   if (L.use_voxel) {
     ONERF_CUDA(cudaFuncSetAttribute(field_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     field_tc_kernel<true><<<blocks, NUM_THREADS, smem, stream>>>(P);

@@ -12,7 +12,7 @@ models = {k: helpers.make_model(w, True, dev) for k, w in sc["weights"].items()}
 emb = helpers.GridModule(sc["grid"]).to(dev)
 n = 65536
 rays, codes = sc["rays"][:n].to(dev), sc["codes"][:n].to(dev)
-buf = torch.zeros(256, dtype=torch.int64, device=dev)
+buf = torch.zeros(1024, dtype=torch.int64, device=dev)
 lib = _lib.load()
 lib.onerf_debug_timeline.argtypes = [ctypes.c_void_p]
 with torch.no_grad():
@@ -34,3 +34,11 @@ for l in range(16):
     for h in range(2):
         a, b, c, d = [t[(l*2+h)*4+k] - t0 for k in range(4)]
         print(f"{names[l]:5s} h{h} | {a:8d} {b:8d} | {c:8d} {d:8d} | {b-a:6d} {d-c:6d} {c-b:6d}")
+
+print("stage: wait_full  issue(8 mma + commit)  gap_to_next")
+prev=None
+for i in range(80):
+    a,b,c=[t[256+i*3+k]-t0 for k in range(3)]
+    if t[256+i*3]==0: break
+    print(f"{i:3d}: start {a:7d} wait {b-a:6d} issue {c-b:6d} gap {(a-prev) if prev is not None else 0:6d}")
+    prev=c
