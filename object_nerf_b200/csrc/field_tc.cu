@@ -1,6 +1,10 @@
 // tcgen05 (5th-gen tensor core) implementation of the fused encode + two-branch MLP for sm_100a.
 //
-// One persistent CTA per SM; a CTA owns one M = 128 tile of consecutive samples at a time.
+// Persistent CTA PAIRS (cluster of 2, one CTA per SM, tcgen05 cta_group::2): each CTA owns one M = 128 tile of
+// consecutive samples at a time (own X, own TMEM), the pair's leader issues M = 256 MMAs for both, and each CTA
+// stages only HALF of every weight slab in its shared memory (the tensor core reads B from both CTAs), which
+// halves the shared-memory and L2 traffic per FLOP - the limiter of the 1-CTA version (tools/ubench/mma_rate.cu:
+// N=128 MMAs run at 67 cycles alone but ~100 when the B slabs are written and read at 64 B/clk each).
 //   warps 0-15 (512 thr)  encode the tile into shared memory (X, bf16, UMMA K-major SWIZZLE_128B atoms) and run
 //                         every layer's epilogue: TMEM accumulator -> registers (tcgen05.ld) -> bias / per-ray
 //                         constant -> LeakyReLU -> bf16x2 -> back into TMEM (tcgen05.st) as the NEXT layer's A
@@ -29,8 +33,8 @@
 namespace {
 
 constexpr int TM = 128;             // samples per tile (UMMA M)
-constexpr int NSTAGE = 3;           // weight ring depth
-constexpr int SLAB_BYTES = 8192;    // 128 rows x 64 B: one half K-slab (32 of K) of an N = 256 layer
+constexpr int NSTAGE = 6;           // weight ring depth
+constexpr int SLAB_BYTES = 4096;    // 64 rows x 64 B: this CTA's half of one half K-slab (32 of K) of an N = 256 layer
 constexpr int STAGE_SLABS = 4;      // a ring stage carries up to 4 consecutive K-slabs (128 of K) of one layer half
 constexpr int STAGE_BYTES = STAGE_SLABS * SLAB_BYTES;
 constexpr int MAX_GROUPS = 6;
@@ -107,7 +111,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
       : "r"(bar), "r"(parity)
@@ -118,7 +122,7 @@ __device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) { 
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.test_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
       : "r"(bar), "r"(parity)
@@ -136,6 +140,25 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       __trap();
     }
   }
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+// arrive on an mbarrier anywhere in the cluster (address from mapa)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 // make generic-proxy shared-memory writes visible to the async proxy (TMA / tcgen05 operand reads)
@@ -160,11 +183,11 @@ __device__ __forceinline__ bool elect_one() {
 }
 
 __device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 
 // D[tmem] (+)= A[smem desc] . B[smem desc]^T, bf16 inputs, fp32 accumulate
@@ -189,23 +212,27 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
 template <bool ACC>
 __device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc) {
   if constexpr (ACC)
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 1;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 1;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
                  "l"(desc_a), "l"(desc_b), "r"(idesc) : "memory");
   else
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, 1, 1;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, 1, 1;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
                  "l"(desc_a), "l"(desc_b), "r"(idesc) : "memory");
 }
 template <bool ACC>
 __device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc) {
   if constexpr (ACC)
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 1;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 1;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
                  "r"(tmem_a), "l"(desc_b), "r"(idesc) : "memory");
   else
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, 1, 1;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, 1, 1;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
                  "r"(tmem_a), "l"(desc_b), "r"(idesc) : "memory");
 }
+// completion of all prior tcgen05.mma of this thread -> arrive on the barrier at this offset in BOTH CTAs of the pair
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  asm volatile(
+      "{\n\t.reg .b16 m;\n\tmov.b16 m, 3;\n\t"
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t}" ::"r"(bar)
+      : "memory");
 }
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
@@ -261,8 +288,8 @@ __device__ __forceinline__ uint64_t make_desc_hl(uint32_t lo, uint32_t hi) {
   return d;
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B bf16, both K-major, M = 128
-__device__ __forceinline__ uint32_t make_idesc(int N) {  // N = columns of ONE mma (a layer half)
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+__device__ __forceinline__ uint32_t make_idesc(int N) {  // N = columns of ONE mma (a layer half); M = 256 (cta_group::2)
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)((2 * TM) >> 4) << 24);
 }
 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
@@ -458,7 +485,7 @@ __device__ __forceinline__ void epilogue_half(const TcLayer& Ly, uint32_t acc_ad
 // MMA issue of one ring stage: CNT K-slabs (2 K-steps each) as straight-line code with immediate offsets.
 //   FROM_H: A from TMEM (a0 = TMEM address of the first slab's packed K columns), else A from shared memory
 //           (a0 = descriptor low word of the first slab; X groups start atom-aligned)
-//   HB16:   bytes >> 4 of one half K-slab in the ring stage (N/2 rows x 64 B)
+//   HB16:   bytes >> 4 of this CTA's part of one half K-slab in the ring stage (N/4 rows x 64 B)
 // ------------------------------------------------------------------------------------------------
 template <bool FROM_H, int CNT, int HB16, bool FIRST>
 __device__ __forceinline__ void issue_stage(uint32_t d_tmem, uint32_t a0, uint32_t b_lo0, uint32_t idesc) {
@@ -499,9 +526,9 @@ __device__ __forceinline__ void issue_stage_cnt(int cnt, bool first, uint32_t d_
 }
 template <bool FROM_H>
 __device__ __forceinline__ void issue_stage_n(int N, int cnt, bool first, uint32_t d_tmem, uint32_t a0, uint32_t b_lo0, uint32_t idesc) {
-  if (N == 256) issue_stage_cnt<FROM_H, 512>(cnt, first, d_tmem, a0, b_lo0, idesc);
-  else if (N == 128) issue_stage_cnt<FROM_H, 256>(cnt, first, d_tmem, a0, b_lo0, idesc);
-  else issue_stage_cnt<FROM_H, 128>(cnt, first, d_tmem, a0, b_lo0, idesc);
+  if (N == 256) issue_stage_cnt<FROM_H, 256>(cnt, first, d_tmem, a0, b_lo0, idesc);
+  else if (N == 128) issue_stage_cnt<FROM_H, 128>(cnt, first, d_tmem, a0, b_lo0, idesc);
+  else issue_stage_cnt<FROM_H, 64>(cnt, first, d_tmem, a0, b_lo0, idesc);
 }
 
 template <bool VOXEL>
@@ -532,17 +559,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_tc_kernel(const __grid_c
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - sbase));
   const float* Pf = reinterpret_cast<const float*>(p.packed);
 
+  const uint32_t cta_rank = cluster_ctarank();        // 0 = leader (issues the pair's MMAs)
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
-      mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_empty + 8 * s, 1);
+      // leader: its own TMA (arrive.expect_tx) + the peer's "my half has landed" remote arrive
+      mbar_init(bar_full + 8 * s, cta_rank == 0 ? 2 : 1);
+      mbar_init(bar_empty + 8 * s, 1);                // multicast tcgen05.commit
     }
-    // compute -> MMA barriers take ONE arrive per warp (after __syncwarp): 512 serialized shared-memory
-    // atomics per phase would cost more than the epilogue math
-    mbar_init(bar_x_ready, NUM_COMPUTE / 32);
+    // compute -> MMA barriers live in the leader and take ONE arrive per compute warp of BOTH CTAs
+    mbar_init(bar_x_ready, 2 * NUM_COMPUTE / 32);
     for (int h = 0; h < 2; ++h) {
-      mbar_init(bar_acc_ready + 8 * h, 1);
-      mbar_init(bar_epi_done + 8 * h, NUM_COMPUTE / 32);
+      mbar_init(bar_acc_ready + 8 * h, 1);            // multicast tcgen05.commit
+      mbar_init(bar_epi_done + 8 * h, 2 * NUM_COMPUTE / 32);
     }
     fence_barrier_init();
   }
@@ -556,11 +584,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_tc_kernel(const __grid_c
     stage_tab[i] = *reinterpret_cast<const uint4*>(&P.stages[i]);
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();          // both CTAs' barriers initialised before any remote arrive / multicast commit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
 
   const int64_t total = (int64_t)p.n_rays * p.S;
   const int64_t n_tiles = (total + TM - 1) / TM;
+  const int64_t n_pairs = (n_tiles + 1) / 2;
+  const int64_t pair0 = blockIdx.x >> 1, pair_step = gridDim.x >> 1;
+  // barriers of the leader, as seen from this CTA
+  const uint32_t ld_x_ready = mapa(bar_x_ready, 0), ld_epi_done = mapa(bar_epi_done, 0), ld_full = mapa(bar_full, 0);
   const uint8_t* blob = reinterpret_cast<const uint8_t*>(p.packed);
 
   if (warp == PRODUCER_WARP) {
@@ -568,16 +601,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_tc_kernel(const __grid_c
     // The whole warp runs the (uniform) loop over the flattened stage program; one elected lane talks to the
     // barriers / TMA.  It runs ahead of the MMA warp by the ring depth, across layers and tiles.
     uint32_t stage = 0, phase = 0;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (int64_t pair = pair0; pair < n_pairs; pair += pair_step) {
       for (int si = 0; si < P.n_stages; ++si) {
         const uint4 raw = stage_tab[si];
-        const uint32_t half_bytes = (raw.w & 0xFFFFu) << 4, cnt = (raw.w >> 16) & 0xFFu;
+        const uint32_t my_bytes = (raw.w & 0xFFFFu) << 4, cnt = (raw.w >> 16) & 0xFFu;   // this CTA's rows of a half-slab
         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
         if (elect_one()) {
-          mbar_expect_tx(bar_full + 8 * stage, cnt * half_bytes);
-          const uint8_t* src = blob + raw.y;
+          mbar_expect_tx(bar_full + 8 * stage, cnt * my_bytes);
+          const uint8_t* src = blob + raw.y + cta_rank * my_bytes;
           for (uint32_t i2 = 0; i2 < cnt; ++i2)
-            tma_bulk_g2s(sB + stage * STAGE_BYTES + i2 * half_bytes, src + (size_t)i2 * raw.z, half_bytes,
+            tma_bulk_g2s(sB + stage * STAGE_BYTES + i2 * my_bytes, src + (size_t)i2 * raw.z, my_bytes,
                          bar_full + 8 * stage);
         }
         __syncwarp();
@@ -590,13 +623,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_tc_kernel(const __grid_c
     // `full` barrier probed BEFORE the current stage's MMAs are issued, so neither latency sits between two
     // bursts of tcgen05.mma.  Barrier waits are executed by all lanes, mma / commit by one elected lane.
     uint32_t stage = 0, phase = 0, x_phase = 0, ed_phase0 = 0, ed_phase1 = 0;
+    if (cta_rank != 0) {
+      // peer CTA: no MMA issue; forward "my half of stage s has landed" to the leader's full barrier
+      for (int64_t pair = pair0; pair < n_pairs; pair += pair_step) {
+        for (int si = 0; si < P.n_stages; ++si) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          if (elect_one()) mbar_arrive_cluster(ld_full + 8 * stage);
+          __syncwarp();
+          if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else {
     int tl_idx = 0;
     uint4 cur = stage_tab[0];
     bool cur_ready = false;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (int64_t pair = pair0; pair < n_pairs; pair += pair_step) {
       for (int si = 0; si < P.n_stages; ++si) {
         const uint32_t flags = cur.w >> 24, cnt = (cur.w >> 16) & 0xFFu, hb16 = cur.w & 0xFFFFu;
-        const bool tl = P.timeline && blockIdx.x == 0 && tile == (int64_t)gridDim.x && lane == 0;
+        const bool tl = P.timeline && blockIdx.x == 0 && pair == pair0 + pair_step && lane == 0;
         if (tl) P.timeline[256 + (tl_idx * 3 + 0)] = clock64();
         if (flags & ST_WAIT_X) { mbar_wait(bar_x_ready, x_phase); x_phase ^= 1; }
         if (flags & ST_WAIT_E0) { mbar_wait(bar_epi_done, ed_phase0); ed_phase0 ^= 1; }
@@ -604,7 +648,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_tc_kernel(const __grid_c
         if (!cur_ready) mbar_wait(bar_full + 8 * stage, phase);
         tc_fence_after();
         if (tl) P.timeline[256 + (tl_idx * 3 + 1)] = clock64();
-        // prefetch the next stage's descriptor and probe its barrier (the stage table wraps around per tile)
+        // prefetch the next stage's descriptor and probe its barrier (the stage table wraps around per tile pair)
         const int sn = (si + 1 == P.n_stages) ? 0 : si + 1;
         const uint4 nxt = stage_tab[sn];
         const uint32_t nstage = (stage + 1 == NSTAGE) ? 0u : stage + 1, nphase = (stage + 1 == NSTAGE) ? phase ^ 1u : phase;
@@ -612,7 +656,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_tc_kernel(const __grid_c
         if (elect_one()) {
           const uint32_t d_tmem = tmem_base + ((flags & ST_HALF1) ? (uint32_t)TM_ACC1 : 0u);
           const uint32_t b_lo0 = (((sB + stage * STAGE_BYTES) >> 4) & 0x3FFFu) | 0x10000u;
-          const int N = (int)(hb16 >> 1);
+          const int N = (int)hb16;                   // per-CTA slab bytes >> 4 == N (N/4 rows x 64 B)
           const uint32_t idesc = make_idesc(N >> 1);
           const bool first = (flags & ST_FIRST) != 0;
           if (flags & ST_FROM_H) issue_stage_n<true>(N, (int)cnt, first, d_tmem, tmem_base + cur.x, b_lo0, idesc);
@@ -626,6 +670,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_tc_kernel(const __grid_c
         cur = nxt; cur_ready = nxt_ready;
       }
     }
+    }
   } else {
     // =============================== encode + epilogue warps ===============================
     const int q = warp & 3, cq = warp >> 2;          // TMEM lane quarter (rows), column quarter
@@ -634,11 +679,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_tc_kernel(const __grid_c
     uint32_t acc_phase0 = 0, acc_phase1 = 0;
     // nothing to drain before the very first layer
     if (lane == 0) {
-      mbar_arrive(bar_epi_done);
-      mbar_arrive(bar_epi_done + 8);
+      mbar_arrive_cluster(ld_epi_done);
+      mbar_arrive_cluster(ld_epi_done + 8);
     }
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      if (P.timeline && blockIdx.x == 0 && tile == (int64_t)gridDim.x && threadIdx.x == 0) P.timeline[201] = clock64();
+    for (int64_t pair = pair0; pair < n_pairs; pair += pair_step) {
+      const int64_t tile = 2 * pair + cta_rank;        // may be == n_tiles (odd tail): a dead tile, nothing written
+      if (P.timeline && blockIdx.x == 0 && pair == pair0 + pair_step && threadIdx.x == 0) P.timeline[201] = clock64();
       const int64_t e = tile * TM + row;
       const bool live = e < total;
       const int ray = live ? (int)(e / p.S) : 0;
@@ -682,8 +728,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_tc_kernel(const __grid_c
       }
       fence_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_x_ready);
-      if (P.timeline && blockIdx.x == 0 && tile == (int64_t)gridDim.x && threadIdx.x == 0) P.timeline[200] = clock64();
+      if (lane == 0) mbar_arrive_cluster(ld_x_ready);
+      if (P.timeline && blockIdx.x == 0 && pair == pair0 + pair_step && threadIdx.x == 0) P.timeline[200] = clock64();
 
       float sigma_part = 0.0f;
       for (int l = 0; l < P.n_layers; ++l) {
@@ -701,15 +747,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_tc_kernel(const __grid_c
           if (h == 0) { mbar_wait(bar_acc_ready, acc_phase0); acc_phase0 ^= 1; }
           else { mbar_wait(bar_acc_ready + 8, acc_phase1); acc_phase1 ^= 1; }
           tc_fence_after();
-          if (P.timeline && blockIdx.x == 0 && tile == (int64_t)gridDim.x && threadIdx.x == 0) P.timeline[(l * 2 + h) * 4 + 2] = clock64();
+          if (P.timeline && blockIdx.x == 0 && pair == pair0 + pair_step && threadIdx.x == 0) P.timeline[(l * 2 + h) * 4 + 2] = clock64();
           if (NC == 32) epilogue_half<32>(Ly, acc_addr, out_addr, bias_tab + l * 256, rc, headw, n, part0, part1, part2);
           else if (NC == 16) epilogue_half<16>(Ly, acc_addr, out_addr, bias_tab + l * 256, rc, headw, n, part0, part1, part2);
           else epilogue_half<8>(Ly, acc_addr, out_addr, bias_tab + l * 256, rc, headw, n, part0, part1, part2);
           // accumulator half h drained, output activations of this half written
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar_epi_done + 8 * h);
-          if (P.timeline && blockIdx.x == 0 && tile == (int64_t)gridDim.x && threadIdx.x == 0) P.timeline[(l * 2 + h) * 4 + 3] = clock64();
+          if (lane == 0) mbar_arrive_cluster(ld_epi_done + 8 * h);
+          if (P.timeline && blockIdx.x == 0 && pair == pair0 + pair_step && threadIdx.x == 0) P.timeline[(l * 2 + h) * 4 + 3] = clock64();
         }
         if (Ly.epi == EPI_HIDDEN_SIGMA) sigma_part = part0;
         if (Ly.epi == EPI_DIR) {
@@ -739,6 +785,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_tc_kernel(const __grid_c
   // ---- teardown ----
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();          // no remote arrive / multicast commit may target a CTA that has exited
   if (warp == MMA_WARP) tmem_dealloc(tmem_base, 512);
 }
 
@@ -819,7 +866,7 @@ int onerf_launch_field_bf16(onerf_ctx* ctx, const FieldParams& fp, cudaStream_t 
         if (gi == t.ngroups - 1) fl |= ST_COMMIT_ACC;
         sd.flags = fl;
         sd.cnt = (uint8_t)cnt;
-        sd.hb16 = (uint16_t)(half_bytes >> 4);
+        sd.hb16 = (uint16_t)(half_bytes >> 5);   // this CTA's rows of the half-slab: N/4 rows x 64 B, >> 4  (== N)
         sd.slab_bytes = slab_bytes;
         const int gslab = from_h ? t.nslab_x + first : first;
         sd.src_off = (uint32_t)(t.img_off + (int64_t)gslab * slab_bytes + (int64_t)h * half_bytes);
@@ -830,15 +877,29 @@ int onerf_launch_field_bf16(onerf_ctx* ctx, const FieldParams& fp, cudaStream_t 
   P.n_stages = ns;
   const int64_t total = (int64_t)fp.n_rays * fp.S;
   const int64_t tiles = (total + TM - 1) / TM;
-  const int blocks = (int)(tiles < ctx->num_sms ? tiles : ctx->num_sms);
+  const int64_t pairs = (tiles + 1) / 2;
+  int blocks = (int)(2 * pairs < (int64_t)(ctx->num_sms & ~1) ? 2 * pairs : (int64_t)(ctx->num_sms & ~1));
   const size_t smem = 1024 + (size_t)P.x_atoms * ATOM_BYTES + NSTAGE * STAGE_BYTES + MAX_LAYERS * 256 * 4 +
                       TM * 4 * 4 * 4 + MAX_STAGES * 16 + 512;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(blocks);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;   // CTA pair: tcgen05 cta_group::2
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
   if (L.use_voxel) {
     ONERF_CUDA(cudaFuncSetAttribute(field_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    field_tc_kernel<true><<<blocks, NUM_THREADS, smem, stream>>>(P);
+    ONERF_CUDA(cudaLaunchKernelEx(&cfg, field_tc_kernel<true>, P));
   } else {
     ONERF_CUDA(cudaFuncSetAttribute(field_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    field_tc_kernel<false><<<blocks, NUM_THREADS, smem, stream>>>(P);
+    ONERF_CUDA(cudaLaunchKernelEx(&cfg, field_tc_kernel<false>, P));
   }
   ONERF_LAUNCH_CHECK(ctx);
   return ONERF_OK;

@@ -316,8 +316,8 @@ def render_rays(weights: Dict[str, dict], grid: Optional[VoxelGrid], rays, codes
     one_pass("coarse", z)
     if n_importance > 0:
         mid = 0.5 * (z[:, :-1] + z[:, 1:])                                            # :302-304
-        z_new = sample_pdf(mid, out["weights_coarse"][:, 1:-1], n_importance,
-                           det=(perturb == 0), u=rand.get("u"))                        # :305-310
+        z_new = sample_pdf(mid, out["weights_coarse"][:, 1:-1].detach(), n_importance,
+                           det=(perturb == 0), u=rand.get("u"))                        # :305-310 (detached, :307)
         one_pass("fine", merge_sorted(z, z_new))                                      # :313
     return out
 
@@ -407,7 +407,7 @@ def render_rays_multi(weights, grid, code_table, rays_list, obj_instance_ids, n_
             n = z.shape[0]
             mid = 0.5 * (z[:, :-1] + z[:, 1:])
             w_i = out["weights_coarse"][out["obj_ids_coarse"] == i].view(n, n_samples)   # :269-271
-            z_new = sample_pdf(mid, w_i[:, 1:-1], n_importance, det=True)
+            z_new = sample_pdf(mid, w_i[:, 1:-1].detach(), n_importance, det=True)
             z_fine.append(merge_sorted(z, z_new))
         rgbs, sigmas = eval_all("fine", z_fine)
         composite_multi(out, "fine", z_fine, rgbs, sigmas, white_back)

@@ -137,3 +137,61 @@ def stage_inputs():
         "pdf_weights": f(wts),
         "pdf_u": f(rng.random((n, 64))),
     }
+
+
+# ---------------------------------------------------------------------------------------------
+# training-step (gradient) case: SURVEY.md §8d config 3 in miniature
+# ---------------------------------------------------------------------------------------------
+GRAD_CASE = dict(_BASE, n_rays=40, perturb=1.0, noise_std=1.0, is_eval=False, frustum_bound_th=0.025,
+                 pass_through=True, seed=300, sigma_gain=4.0, sigma_bias=0.5)
+LOSS_CONF = dict(color_loss_weight=1.0, depth_loss_weight=0.1, opacity_loss_weight=100.0,
+                 instance_color_loss_weight=1.0, instance_depth_loss_weight=0.1)   # default_conf.yml:61-66 + scannet override
+GRAD_SAMPLES = 256   # entries sampled per parameter tensor in the fixture
+
+
+def build_grad_case():
+    c = GRAD_CASE
+    inp = build_render_case(c)
+    n = c["n_rays"]
+    rng = np.random.default_rng(c["seed"] + 9)
+    ids = rng.choice([4, 6], size=n)
+    inp["instance_ids"] = torch.from_numpy(ids).view(n, 1)
+    inp["code_table"] = synth.make_codes(c["seed"] + 2)
+    inp["batch"] = {
+        "rgbs": torch.from_numpy(rng.random((n, 3)).astype(np.float32)),
+        "depths": torch.from_numpy(rng.uniform(0.3, 2.5, size=n).astype(np.float32)),
+        "valid_mask": torch.from_numpy(rng.random(n) < 0.9),
+        "instance_mask": torch.from_numpy(rng.random(n) < 0.5),
+        "instance_mask_weight": torch.from_numpy(np.where(rng.random(n) < 0.5, 1.0, 0.05).astype(np.float32)),
+    }
+    return inp
+
+
+def total_loss(out, batch, conf=LOSS_CONF):
+    """The reference's TotalLoss (models/losses.py:5-135) restated for tests: masked MSEs over coarse + fine maps."""
+    vm = batch["valid_mask"].view(-1)
+    im = batch["instance_mask"].view(-1)
+    imw = batch["instance_mask_weight"].view(-1)
+    tgt_rgb, tgt_d = batch["rgbs"].view(-1, 3), batch["depths"].view(-1)
+    loss = 0.0
+    for typ in ("coarse", "fine"):
+        if f"rgb_{typ}" not in out:
+            continue
+        loss = loss + conf["color_loss_weight"] * ((out[f"rgb_{typ}"][vm] - tgt_rgb[vm]) ** 2).mean()
+        dm = vm & (tgt_d > 0)
+        loss = loss + conf["depth_loss_weight"] * ((out[f"depth_{typ}"][dm] - tgt_d[dm]) ** 2).mean()
+        loss = loss + conf["opacity_loss_weight"] * (
+            ((out[f"opacity_instance_{typ}"][vm].clamp(0, 1) - im[vm].float()) ** 2) * imw[vm]).mean()
+        m2 = vm & im
+        loss = loss + conf["instance_color_loss_weight"] * (
+            ((out[f"rgb_instance_{typ}"][m2] - tgt_rgb[m2]) ** 2) * imw[m2][:, None]).mean()
+        m3 = dm & im
+        loss = loss + conf["instance_depth_loss_weight"] * (
+            ((out[f"depth_instance_{typ}"][m3] - tgt_d[m3]) ** 2) * imw[m3]).mean()
+    return loss
+
+
+def sample_indices(name, numel):
+    import zlib
+    rng = np.random.default_rng(zlib.crc32(name.encode()))
+    return torch.from_numpy(rng.integers(0, numel, size=min(GRAD_SAMPLES, numel)))

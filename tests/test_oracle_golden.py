@@ -86,3 +86,44 @@ def test_render_rays_multi(golden, name):
     assert set(out) == set(g), (sorted(out), sorted(g))
     for k in g:
         assert_same(out[k], g[k], k, exact=True)
+
+
+def test_training_step_gradients_match_reference(golden):
+    """Oracle autograd (torch CPU) vs the reference's backward through render_rays + TotalLoss
+    (fixture: loss, and per parameter tensor the L2 norm, the sum and 256 sampled entries)."""
+    g = golden("grad_train_step")
+    c = cases.GRAD_CASE
+    inp = cases.build_grad_case()
+    leaves = {}
+
+    def leaf(name, t):
+        t = t.clone().requires_grad_(True)
+        leaves[name] = t
+        return t
+
+    weights = {typ: {k: (leaf(f"{typ}.{helpers_name(k)}.weight", W), leaf(f"{typ}.{helpers_name(k)}.bias", b))
+                     for k, (W, b) in w.items()} for typ, w in inp["weights"].items()}
+    table = leaf("voxel", inp["grid"]["table"])
+    code_table = leaf("codes", inp["code_table"])
+    gd = inp["grid"]
+    grid = O.VoxelGrid(gd["offset"], gd["voxel_size"], gd["shape"].tolist(), gd["idx_map"], table)
+    codes = code_table[inp["instance_ids"].view(-1)]
+    out = O.render_rays(weights, grid, inp["rays"], codes, n_samples=c["n_samples"], perturb=c["perturb"],
+                        noise_std=c["noise_std"], n_importance=c["n_importance"], frustum_bound_th=c["frustum_bound_th"],
+                        pass_through_mask=inp["pass_through_mask"], is_eval=False, rand=inp["rand"])
+    loss = cases.total_loss(out, inp["batch"])
+    assert abs(loss.item() - g["loss"].item()) <= 1e-5 * abs(g["loss"].item())
+    loss.backward()
+    for name, t in leaves.items():
+        gr = t.grad.reshape(-1)
+        ref_norm = g[name + "|norm"].item()
+        assert abs(gr.norm().item() - ref_norm) <= 1e-4 * max(ref_norm, 1e-6), name
+        idx = cases.sample_indices(name, gr.numel())
+        assert torch.allclose(gr[idx], g[name + "|samples"], rtol=1e-3, atol=1e-5 * max(ref_norm, 1e-6)), name
+    nz = torch.nonzero(table.grad.abs().sum(1)).view(-1)
+    assert torch.equal(nz, g["voxel|nonzero_rows"])
+
+
+def helpers_name(k):
+    from tests.helpers import REF_NAMES
+    return REF_NAMES[k]

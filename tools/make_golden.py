@@ -187,6 +187,46 @@ def gen_multi_cases():
         save("multi_" + name, **out)
 
 
+def gen_grad_case():
+    """Training step through the REAL reference: render_rays (train mode, injected RNG) -> reference TotalLoss ->
+    backward.  The fixture keeps the loss and, per parameter tensor, its L2 norm, sum and sampled entries."""
+    from models.losses import TotalLoss
+    from models.code_library import CodeLibrary
+    c = cases.GRAD_CASE
+    inp = cases.build_grad_case()
+    models = {"coarse": ref_model(inp["weights"]["coarse"], True).train(),
+              "fine": ref_model(inp["weights"]["fine"], True).train()}
+    emb = ref_voxel_embedding(inp["grid"])
+    lib = CodeLibrary(R.default_model_config())
+    with torch.no_grad():
+        lib.embedding_instance.weight.copy_(inp["code_table"])
+    codes = lib({"instance_ids": inp["instance_ids"]})["embedding_instance"]
+    r = inp["rand"]
+    with InjectRandom([r["jitter"]], [r["u"]], [r["noise_scene_coarse"], r["noise_obj_coarse"], r["noise_scene_fine"],
+                                               r["noise_obj_fine"]]):
+        out = ref_render_rays(models, {"xyz": emb, "dir": Embedding(3, 4)}, inp["rays"], N_samples=c["n_samples"],
+                              use_disp=False, perturb=c["perturb"], noise_std=c["noise_std"],
+                              N_importance=c["n_importance"], chunk=32768, white_back=False,
+                              embedding_instance=codes, frustum_bound_th=c["frustum_bound_th"],
+                              pass_through_mask=inp["pass_through_mask"], rays_in_bbox=False, is_eval=False)
+    loss, _ = TotalLoss(R.AttrDict(cases.LOSS_CONF))(out, inp["batch"])
+    # our restatement of the loss must agree with the reference's
+    assert abs(cases.total_loss(out, inp["batch"]).item() - loss.item()) < 1e-5 * max(1.0, abs(loss.item()))
+    loss.backward()
+    fix = {"loss": loss.detach()}
+    named = [(f"{typ}.{k}", p) for typ, m in models.items() for k, p in m.named_parameters()]
+    named += [("codes", lib.embedding_instance.weight), ("voxel", emb.embedding_space_ftr.weight)]
+    for name, p in named:
+        g = p.grad.reshape(-1)
+        fix[name + "|norm"] = g.norm()
+        fix[name + "|sum"] = g.sum()
+        fix[name + "|samples"] = g[cases.sample_indices(name, g.numel())]
+    nz = torch.nonzero(emb.embedding_space_ftr.weight.grad.abs().sum(1)).view(-1)
+    fix["voxel|nonzero_rows"] = nz
+    save("grad_train_step", **fix)
+    print("loss", loss.item(), "voxel rows touched", nz.numel())
+
+
 def gen_gridbuild():
     """Cold path pin: the reference's EmbeddingVoxel constructor on a synthetic cloud (ScanNet-0113-like
     voxel_size / scale_factor / scene_center, config/scannet_base_0113_multi.yml:7-11,43-44)."""
@@ -202,6 +242,7 @@ def gen_gridbuild():
 if __name__ == "__main__":
     torch.set_num_threads(8)
     gen_gridbuild()
+    gen_grad_case()
     gen_stage_cases()
     gen_render_cases()
     gen_multi_cases()
