@@ -133,6 +133,10 @@ typedef struct onerf_field_args {
   float* obj_out;          /* same for the object branch; iff want_object */
   int64_t out_stride;      /* >= S, in samples */
   float* ray_const;        /* workspace, n_rays * ONERF_RAY_CONST_FLOATS floats */
+  /* backward support (ONERF_PREC_FP32 only): if non-NULL, 17 row-major [n_rays*S x width] matrices receiving the
+   * activations of the forward: [0] X (384 voxel / 64 plain), [1..8] scene hidden 1..8 (256), [9] scene final (256),
+   * [10] scene dir (128), [11..14] object hidden 1..4 (128), [15] object final (128), [16] object dir (64). */
+  float* const* activations;
 } onerf_field_args;
 #define ONERF_RAY_CONST_FLOATS 448
 
@@ -161,6 +165,45 @@ typedef struct onerf_composite_args {
 } onerf_composite_args;
 
 int onerf_composite(onerf_ctx* ctx, const onerf_composite_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Backward building blocks (what loss.backward() does in the reference, train.py:180).
+ * fp32.  object_nerf_b200/backward.py chains them into the gradient of render_rays.
+ * ------------------------------------------------------------------------------------------- */
+
+/* Gradient of onerf_composite w.r.t. the per-sample fields: fwd = the forward's arguments (noise buffers required when
+ * noise_std > 0), depth_scene = forward scene depth (occlusion mask), g_* = upstream gradients of the maps (NULL = 0);
+ * dscene / dobj (N,S,4) = d(r,g,b,sigma).  models/rendering.py:139-229 under autograd. */
+int onerf_composite_bwd(onerf_ctx* ctx, const onerf_composite_args* fwd, const float* depth_scene, const float* g_rgb,
+                        const float* g_depth, const float* g_opacity, const float* g_rgb_inst, const float* g_depth_inst,
+                        const float* g_opacity_inst, float* dscene, float* dobj, void* stream);
+
+/* C[M x N] (+)= op(A) . B in fp32; B [K x N] and C row-major; trans_a = 0: A [M x K]; 1: A [K x M] (reduction over
+ * A's rows, split over CTAs, atomics).  Used for dgrad (dIn = dZ W) and wgrad (dW += dZ^T In) of every nn.Linear. */
+int onerf_gemm(onerf_ctx* ctx, const float* A, int lda, int trans_a, const float* B, int ldb, float* C, int ldc, int M,
+               int N, int K, int accumulate, void* stream);
+
+/* d <- d * (h > 0 ? 1 : 0.01): LeakyReLU backward from the layer OUTPUT (nn.LeakyReLU(inplace=True), nerf_model.py:38). */
+int onerf_leaky_bwd(onerf_ctx* ctx, float* d, int ld_d, const float* h, int ld_h, int64_t rows, int cols, void* stream);
+
+/* dA (n,4) = (d_rgb * rgb * (1 - rgb), d_sigma) from dfield (n,4) and the forward field output (n,4): sigmoid head. */
+int onerf_head_bwd(onerf_ctx* ctx, const float* dfield, const float* field, float* dA, int64_t n, void* stream);
+
+/* out[r][c] = sum over the S consecutive rows of ray r of in (per-ray-constant terms: dir / code columns). */
+int onerf_segment_sum(onerf_ctx* ctx, const float* in, int ld_in, float* out, int ld_out, int n_rays, int n_samples,
+                      int cols, void* stream);
+
+/* out[c] += sum over rows of in[r][c] (bias gradients). */
+int onerf_colsum(onerf_ctx* ctx, const float* in, int ld, int64_t rows, int cols, float* out, void* stream);
+
+/* PE4 of the ray directions, (N,8) -> (N,27) (models/embedding_helper.py:57-74 on rays_d). */
+int onerf_dir_encode(onerf_ctx* ctx, const float* rays, int n_rays, float* out, void* stream);
+
+/* Encoding backward: dX [n_chunk x ldx] (X layout) -> scatter-add into table_grad (n_rows,24); X holds the forward's
+ * sin/cos values; rays/z (N,8)/(N,S) and sample0 locate the chunk's samples.  models/embedding_helper.py:354-409. */
+int onerf_encode_bwd(onerf_ctx* ctx, const onerf_grid* grid, const float* rays, const float* z, int n_rays, int n_samples,
+                     const float* X, const float* dX, int ldx, int64_t sample0, int64_t n_chunk, float* table_grad,
+                     void* stream);
 
 /* Joint depth sort over all objects' samples + compositing, render_tools/multi_rendering.py:96-157.
  * Inputs are object-major: z_all (n_obj, N, S), field_all (n_obj, N, S, 4); the reference's concatenated

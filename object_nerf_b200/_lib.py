@@ -24,6 +24,8 @@ EXPORTS = [
     "onerf_abi_version", "onerf_last_error", "onerf_ctx_create", "onerf_ctx_destroy",
     "onerf_ctx_launch_count", "onerf_packed_weights_bytes", "onerf_pack_weights", "onerf_sample_coarse",
     "onerf_sample_pdf_merge", "onerf_sample_pdf", "onerf_encode", "onerf_field_fwd", "onerf_composite", "onerf_composite_multi",
+    "onerf_composite_bwd", "onerf_gemm", "onerf_leaky_bwd", "onerf_head_bwd", "onerf_segment_sum", "onerf_colsum",
+    "onerf_dir_encode", "onerf_encode_bwd",
 ]
 
 _p = C.c_void_p
@@ -40,6 +42,7 @@ class FieldArgs(C.Structure):
         ("want_scene", C.c_int), ("want_object", C.c_int), ("precision", C.c_int),
         ("mute_zero_rays", C.c_int), ("boxes", _p), ("n_boxes", C.c_int),
         ("scene_out", _p), ("obj_out", _p), ("out_stride", C.c_int64), ("ray_const", _p),
+        ("activations", C.POINTER(_p)),
     ]
 
 
@@ -96,6 +99,14 @@ def load() -> C.CDLL:
         lib.onerf_field_fwd.argtypes = [_p, C.POINTER(FieldArgs), _p]
         lib.onerf_composite.argtypes = [_p, C.POINTER(CompositeArgs), _p]
         lib.onerf_composite_multi.argtypes = [_p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_int, _p, _p, _p, _p, _p, _p, _p, _p]
+        lib.onerf_composite_bwd.argtypes = [_p, C.POINTER(CompositeArgs), _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]
+        lib.onerf_gemm.argtypes = [_p, _p, C.c_int, C.c_int, _p, C.c_int, _p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _p]
+        lib.onerf_leaky_bwd.argtypes = [_p, _p, C.c_int, _p, C.c_int, C.c_int64, C.c_int, _p]
+        lib.onerf_head_bwd.argtypes = [_p, _p, _p, _p, C.c_int64, _p]
+        lib.onerf_segment_sum.argtypes = [_p, _p, C.c_int, _p, C.c_int, C.c_int, C.c_int, C.c_int, _p]
+        lib.onerf_colsum.argtypes = [_p, _p, C.c_int, C.c_int64, C.c_int, _p, _p]
+        lib.onerf_dir_encode.argtypes = [_p, _p, C.c_int, _p, _p]
+        lib.onerf_encode_bwd.argtypes = [_p, C.POINTER(Grid), _p, _p, C.c_int, C.c_int, _p, _p, C.c_int, C.c_int64, C.c_int64, _p, _p]
         if lib.onerf_abi_version() != 1:
             raise RuntimeError("libonerf_sm100.so ABI version mismatch")
         _lib = lib

@@ -75,6 +75,14 @@ extern "C" int onerf_field_fwd(onerf_ctx* ctx, const onerf_field_args* a, void* 
   p.boxes = a->boxes; p.n_boxes = a->n_boxes;
   p.scene_out = a->scene_out; p.obj_out = a->obj_out; p.out_stride = a->out_stride;
   p.ray_const = a->ray_const;
+  if (a->activations) {
+    ONERF_UNSUPPORTED(a->precision != ONERF_PREC_FP32, "activation dump is built for ONERF_PREC_FP32 only");
+    ONERF_UNSUPPORTED(a->z_stride != a->n_samples || a->out_stride != a->n_samples, "activation dump needs dense z / outputs");
+    for (int i = 0; i < 17; ++i) ONERF_CHECK_ARG(a->activations[i], "null activation matrix");
+    p.dump_x = a->activations[0];
+    for (int i = 0; i < 10; ++i) p.dump_s[i] = a->activations[1 + i];
+    for (int i = 0; i < 6; ++i) p.dump_o[i] = a->activations[11 + i];
+  }
   int rc = onerf_launch_ray_const(ctx, p, stream);
   if (rc != ONERF_OK) return rc;
   if (a->precision == ONERF_PREC_FP32) return onerf_launch_field_fp32(ctx, p, stream);

@@ -22,6 +22,12 @@ struct FieldParams {
   float* obj_out;
   int64_t out_stride;
   float* ray_const;       // (N, ONERF_RAY_CONST_FLOATS)
+  // backward support (FFMA kernel only): dump every layer's activations as [samples x width] row-major matrices
+  //   dump_x: X (KO wide);  dump_s[0..7] scene hidden (256), [8] final (256), [9] dir (128);
+  //   dump_o[0..3] object hidden (128), [4] final (128), [5] dir (64).  All null = no dump.
+  float* dump_x;
+  float* dump_s[10];
+  float* dump_o[6];
 };
 
 // removed-object mask: inside any box <=> lo <= A p + t <= hi (inclusive), utils/bbox_utils.py:158-207

@@ -52,12 +52,13 @@ __device__ __forceinline__ void gemm_seg(const float* __restrict__ A, int K, con
 }
 
 // One layer: out[n][s] = act( sum_seg A_seg . Wt + bias ), bias per column (bias != null) or per
-// ray (rc_base >= 0: ray_const[ray(s)][rc_base + n]).
+// ray (rc_base >= 0: ray_const[ray(s)][rc_base + n]).  dump != null: also store the outputs as rows of a
+// [samples x N] row-major matrix (backward support), first row = sample e0 of the tile.
 template <int NO>
 __device__ __forceinline__ void layer(const float* A0, int K0, const float* A1, int K1,
                                       const float* __restrict__ Wt, const float* __restrict__ bias,
                                       const float* __restrict__ ray_const, const int* s_ray, int rc_base,
-                                      bool leaky, float* out) {
+                                      bool leaky, float* out, float* dump = nullptr, int64_t e0 = 0, int64_t total = 0) {
   const int N = 32 * NO;
   const int sg = threadIdx.x >> 5, og = threadIdx.x & 31;
   float acc[4][NO];
@@ -70,7 +71,6 @@ __device__ __forceinline__ void layer(const float* A0, int K0, const float* A1, 
 #pragma unroll
   for (int o = 0; o < NO; ++o) {
     const int n = og * NO + o;
-    float v[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const float bv = (rc_base >= 0)
@@ -78,9 +78,20 @@ __device__ __forceinline__ void layer(const float* A0, int K0, const float* A1, 
                            : __ldg(bias + n);
       float t = acc[i][o] + bv;
       if (leaky) t = t > 0.0f ? t : t * kLeaky;
-      v[i] = t;
+      acc[i][o] = t;
     }
-    *reinterpret_cast<float4*>(out + n * TS + 4 * sg) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(out + n * TS + 4 * sg) = make_float4(acc[0][o], acc[1][o], acc[2][o], acc[3][o]);
+  }
+  if (dump) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int64_t e = e0 + 4 * sg + i;
+      if (e < total) {
+        float* d = dump + e * N + og * NO;   // a warp writes one contiguous row of N floats
+#pragma unroll
+        for (int o = 0; o < NO; ++o) d[o] = acc[i][o];
+      }
+    }
   }
 }
 
@@ -168,25 +179,31 @@ __global__ void __launch_bounds__(256) field_fp32_kernel(FieldParams p) {
       }
     }
     __syncthreads();
+    if (p.dump_x) {
+      for (int idx = threadIdx.x; idx < KO * TS; idx += blockDim.x) {
+        const int k = idx / TS, sidx = idx % TS;
+        if (e0 + sidx < total) p.dump_x[(e0 + sidx) * KO + k] = X[k * TS + sidx];
+      }
+    }
     const float* rc = p.ray_const;
     // ---------------- scene branch (models/nerf_model.py:97-121) ----------------
     if (p.want_scene) {
-      layer<8>(X, KX, nullptr, 0, Pf + L.g[G_S0].wt_off, Pf + L.g[G_S0].bias_off, rc, s_ray, -1, true, H0); __syncthreads();
-      layer<8>(H0, 256, nullptr, 0, Pf + L.g[G_S1].wt_off, Pf + L.g[G_S1].bias_off, rc, s_ray, -1, true, H1); __syncthreads();
-      layer<8>(H1, 256, nullptr, 0, Pf + L.g[G_S2].wt_off, Pf + L.g[G_S2].bias_off, rc, s_ray, -1, true, H0); __syncthreads();
-      layer<8>(H0, 256, nullptr, 0, Pf + L.g[G_S3].wt_off, Pf + L.g[G_S3].bias_off, rc, s_ray, -1, true, H1); __syncthreads();
-      layer<8>(X, KX, H1, 256, Pf + L.g[G_S4].wt_off, Pf + L.g[G_S4].bias_off, rc, s_ray, -1, true, H0); __syncthreads();
-      layer<8>(H0, 256, nullptr, 0, Pf + L.g[G_S5].wt_off, Pf + L.g[G_S5].bias_off, rc, s_ray, -1, true, H1); __syncthreads();
-      layer<8>(H1, 256, nullptr, 0, Pf + L.g[G_S6].wt_off, Pf + L.g[G_S6].bias_off, rc, s_ray, -1, true, H0); __syncthreads();
-      layer<8>(H0, 256, nullptr, 0, Pf + L.g[G_S7].wt_off, Pf + L.g[G_S7].bias_off, rc, s_ray, -1, true, H1); __syncthreads();
+      layer<8>(X, KX, nullptr, 0, Pf + L.g[G_S0].wt_off, Pf + L.g[G_S0].bias_off, rc, s_ray, -1, true, H0, p.dump_s[0], e0, total); __syncthreads();
+      layer<8>(H0, 256, nullptr, 0, Pf + L.g[G_S1].wt_off, Pf + L.g[G_S1].bias_off, rc, s_ray, -1, true, H1, p.dump_s[1], e0, total); __syncthreads();
+      layer<8>(H1, 256, nullptr, 0, Pf + L.g[G_S2].wt_off, Pf + L.g[G_S2].bias_off, rc, s_ray, -1, true, H0, p.dump_s[2], e0, total); __syncthreads();
+      layer<8>(H0, 256, nullptr, 0, Pf + L.g[G_S3].wt_off, Pf + L.g[G_S3].bias_off, rc, s_ray, -1, true, H1, p.dump_s[3], e0, total); __syncthreads();
+      layer<8>(X, KX, H1, 256, Pf + L.g[G_S4].wt_off, Pf + L.g[G_S4].bias_off, rc, s_ray, -1, true, H0, p.dump_s[4], e0, total); __syncthreads();
+      layer<8>(H0, 256, nullptr, 0, Pf + L.g[G_S5].wt_off, Pf + L.g[G_S5].bias_off, rc, s_ray, -1, true, H1, p.dump_s[5], e0, total); __syncthreads();
+      layer<8>(H1, 256, nullptr, 0, Pf + L.g[G_S6].wt_off, Pf + L.g[G_S6].bias_off, rc, s_ray, -1, true, H0, p.dump_s[6], e0, total); __syncthreads();
+      layer<8>(H0, 256, nullptr, 0, Pf + L.g[G_S7].wt_off, Pf + L.g[G_S7].bias_off, rc, s_ray, -1, true, H1, p.dump_s[7], e0, total); __syncthreads();
       float sigma = 0.0f;
       if (threadIdx.x < TS) {
         const int s = threadIdx.x;
         sigma = __ldg(Pf + L.sigma_b);
         for (int k = 0; k < 256; ++k) sigma = fmaf(H1[k * TS + s], __ldg(Pf + L.sigma_w + k), sigma);
       }
-      layer<8>(H1, 256, nullptr, 0, Pf + L.g[G_SFIN].wt_off, Pf + L.g[G_SFIN].bias_off, rc, s_ray, -1, false, H0); __syncthreads();
-      layer<4>(H0, 256, nullptr, 0, Pf + L.g[G_SDIR].wt_off, nullptr, rc, s_ray, RC_SDIR, true, H1); __syncthreads();
+      layer<8>(H1, 256, nullptr, 0, Pf + L.g[G_SFIN].wt_off, Pf + L.g[G_SFIN].bias_off, rc, s_ray, -1, false, H0, p.dump_s[8], e0, total); __syncthreads();
+      layer<4>(H0, 256, nullptr, 0, Pf + L.g[G_SDIR].wt_off, nullptr, rc, s_ray, RC_SDIR, true, H1, p.dump_s[9], e0, total); __syncthreads();
       if (threadIdx.x < TS) {
         const int s = threadIdx.x;
         const int64_t e = e0 + s;
@@ -208,18 +225,18 @@ __global__ void __launch_bounds__(256) field_fp32_kernel(FieldParams p) {
     }
     // ---------------- object branch (models/nerf_model.py:123-152) ----------------
     if (p.want_object) {
-      layer<4>(X, KO, nullptr, 0, Pf + L.g[G_O0].wt_off, nullptr, rc, s_ray, RC_OL0, true, H0); __syncthreads();
-      layer<4>(H0, 128, nullptr, 0, Pf + L.g[G_O1].wt_off, Pf + L.g[G_O1].bias_off, rc, s_ray, -1, true, H1); __syncthreads();
-      layer<4>(X, KO, H1, 128, Pf + L.g[G_O2].wt_off, nullptr, rc, s_ray, RC_OL2, true, H0); __syncthreads();
-      layer<4>(H0, 128, nullptr, 0, Pf + L.g[G_O3].wt_off, Pf + L.g[G_O3].bias_off, rc, s_ray, -1, true, H1); __syncthreads();
+      layer<4>(X, KO, nullptr, 0, Pf + L.g[G_O0].wt_off, nullptr, rc, s_ray, RC_OL0, true, H0, p.dump_o[0], e0, total); __syncthreads();
+      layer<4>(H0, 128, nullptr, 0, Pf + L.g[G_O1].wt_off, Pf + L.g[G_O1].bias_off, rc, s_ray, -1, true, H1, p.dump_o[1], e0, total); __syncthreads();
+      layer<4>(X, KO, H1, 128, Pf + L.g[G_O2].wt_off, nullptr, rc, s_ray, RC_OL2, true, H0, p.dump_o[2], e0, total); __syncthreads();
+      layer<4>(H0, 128, nullptr, 0, Pf + L.g[G_O3].wt_off, Pf + L.g[G_O3].bias_off, rc, s_ray, -1, true, H1, p.dump_o[3], e0, total); __syncthreads();
       float sigma = 0.0f;
       if (threadIdx.x < TS) {
         const int s = threadIdx.x;
         sigma = __ldg(Pf + L.osigma_b);
         for (int k = 0; k < 128; ++k) sigma = fmaf(H1[k * TS + s], __ldg(Pf + L.osigma_w + k), sigma);
       }
-      layer<4>(H1, 128, nullptr, 0, Pf + L.g[G_OFIN].wt_off, Pf + L.g[G_OFIN].bias_off, rc, s_ray, -1, false, H0); __syncthreads();
-      layer<2>(H0, 128, nullptr, 0, Pf + L.g[G_ODIR].wt_off, nullptr, rc, s_ray, RC_ODIR, true, H1); __syncthreads();
+      layer<4>(H1, 128, nullptr, 0, Pf + L.g[G_OFIN].wt_off, Pf + L.g[G_OFIN].bias_off, rc, s_ray, -1, false, H0, p.dump_o[4], e0, total); __syncthreads();
+      layer<2>(H0, 128, nullptr, 0, Pf + L.g[G_ODIR].wt_off, nullptr, rc, s_ray, RC_ODIR, true, H1, p.dump_o[5], e0, total); __syncthreads();
       if (threadIdx.x < TS) {
         const int s = threadIdx.x;
         const int64_t e = e0 + s;

@@ -111,7 +111,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
       : "r"(bar), "r"(parity)
@@ -122,7 +122,7 @@ __device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) { 
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.test_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
       : "r"(bar), "r"(parity)
@@ -156,9 +156,12 @@ __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
-// arrive on an mbarrier anywhere in the cluster (address from mapa)
+// arrive on an mbarrier anywhere in the cluster (address from mapa).  Default .release.cta semantics, as CUTLASS's
+// ClusterBarrier::arrive(cta_id): nothing is handed over through generic memory (operands live in each CTA's own
+// TMEM / shared memory and are read by the tensor core; tcgen05 fences order them), and cluster-scope
+// release / acquire would flush L1 on every epilogue step.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 // make generic-proxy shared-memory writes visible to the async proxy (TMA / tcgen05 operand reads)
@@ -645,6 +648,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_tc_kernel(const __grid_c
         if (flags & ST_WAIT_X) { mbar_wait(bar_x_ready, x_phase); x_phase ^= 1; }
         if (flags & ST_WAIT_E0) { mbar_wait(bar_epi_done, ed_phase0); ed_phase0 ^= 1; }
         if (flags & ST_WAIT_E1) { mbar_wait(bar_epi_done + 8, ed_phase1); ed_phase1 ^= 1; }
+        if (tl) P.timeline[640 + tl_idx] = clock64() * 256 + (long long)(flags & 0xff);
         if (!cur_ready) mbar_wait(bar_full + 8 * stage, phase);
         tc_fence_after();
         if (tl) P.timeline[256 + (tl_idx * 3 + 1)] = clock64();
@@ -747,7 +751,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_tc_kernel(const __grid_c
           if (h == 0) { mbar_wait(bar_acc_ready, acc_phase0); acc_phase0 ^= 1; }
           else { mbar_wait(bar_acc_ready + 8, acc_phase1); acc_phase1 ^= 1; }
           tc_fence_after();
-          if (P.timeline && blockIdx.x == 0 && pair == pair0 + pair_step && threadIdx.x == 0) P.timeline[(l * 2 + h) * 4 + 2] = clock64();
+          if (P.timeline && blockIdx.x < 2 && pair == pair0 + pair_step && threadIdx.x == 0) P.timeline[768 * blockIdx.x + (l * 2 + h) * 4 + 2] = clock64();
           if (NC == 32) epilogue_half<32>(Ly, acc_addr, out_addr, bias_tab + l * 256, rc, headw, n, part0, part1, part2);
           else if (NC == 16) epilogue_half<16>(Ly, acc_addr, out_addr, bias_tab + l * 256, rc, headw, n, part0, part1, part2);
           else epilogue_half<8>(Ly, acc_addr, out_addr, bias_tab + l * 256, rc, headw, n, part0, part1, part2);
@@ -755,7 +759,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_tc_kernel(const __grid_c
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(ld_epi_done + 8 * h);
-          if (P.timeline && blockIdx.x == 0 && pair == pair0 + pair_step && threadIdx.x == 0) P.timeline[(l * 2 + h) * 4 + 3] = clock64();
+          if (P.timeline && blockIdx.x < 2 && pair == pair0 + pair_step && threadIdx.x == 0) P.timeline[768 * blockIdx.x + (l * 2 + h) * 4 + 3] = clock64();
         }
         if (Ly.epi == EPI_HIDDEN_SIGMA) sigma_part = part0;
         if (Ly.epi == EPI_DIR) {

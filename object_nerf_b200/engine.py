@@ -184,7 +184,7 @@ def encode(xyz, grid: Optional[GridBuffers]):
 
 def field(rays, z, packed, grid: Optional[GridBuffers], codes=None, code_row=None, want_scene=True,
           want_object=True, precision=None, xyz=None, mute_zero_rays=False, boxes=None, scene_out=None,
-          obj_out=None, z_stride=None, out_stride=None, n_samples=None):
+          obj_out=None, z_stride=None, out_stride=None, n_samples=None, activations=None):
     """Fused encode + MLP.  Returns (scene_out, obj_out), each (N,S,4) = rgb,sigma (or None).
     z / outputs may be column blocks of wider arrays (z_stride / out_stride, in samples)."""
     rays = _f32(rays)
@@ -218,6 +218,7 @@ def field(rays, z, packed, grid: Optional[GridBuffers], codes=None, code_row=Non
     a.obj_out = obj_out.data_ptr() if want_object else None
     a.out_stride = out_stride
     a.ray_const = ray_const.data_ptr()
+    a.activations = activations      # (c_void_p * 17) array or None: FFMA kernel dumps per-layer activations (backward)
     if PROFILE_EVENTS is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

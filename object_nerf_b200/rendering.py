@@ -87,6 +87,55 @@ def inference_model(results: Dict[str, Any], model, embeddings: Dict[str, Any], 
     return
 
 
+def _render_forward(cfg, rays, codes, keep=False):
+    """The whole forward of render_rays on the CUDA kernels.  keep=True also returns what the backward needs."""
+    rand = cfg["rand"]
+    perturb, noise_std = cfg["perturb"], cfg["noise_std"]
+    fi = cfg["forward_instance"]
+    emb_xyz = cfg["embeddings"]["xyz"]
+    use_voxel = _is_voxel(emb_xyz)
+    grid = _grid_of(emb_xyz)
+    seed = engine.new_seed() if (perturb > 0 or noise_std > 0) else 0
+    z = engine.sample_coarse(rays, cfg["N_samples"], cfg["use_disp"], perturb, rand.get("jitter"), seed)
+    results: Dict[str, Any] = {}
+    saved: Dict[str, Any] = {}
+
+    def one_pass(typ, z_vals, seed_off):
+        model = cfg["models"][typ]
+        packed = engine.packed_for(model, use_voxel)
+        scene, obj = engine.field(rays, z_vals, packed, grid, codes=codes if fi else None, want_scene=True,
+                                  want_object=fi, precision=cfg["precision"])
+        ns, no = rand.get(f"noise_scene_{typ}"), rand.get(f"noise_obj_{typ}")
+        if keep and noise_std > 0:      # the backward replays the noise: draw it into buffers instead of in-kernel
+            ns = ns if ns is not None else torch.randn_like(z_vals)
+            no = no if (no is not None or not fi) else torch.randn_like(z_vals)
+        out = engine.composite(z_vals, scene, obj, noise_std=noise_std, white_back=cfg["white_back"],
+                               is_eval=cfg["is_eval"], zero_last_delta=cfg["zero_last_delta"],
+                               rays_in_bbox=cfg["rays_in_bbox"], frustum_bound_th=cfg["frustum_bound_th"],
+                               pass_through_mask=cfg["pass_through_mask"], noise_scene=ns, noise_obj=no,
+                               seed=seed + seed_off)
+        results[f"weights_{typ}"] = out["weights"]
+        results[f"opacity_{typ}"] = out["opacity"]
+        results[f"z_vals_{typ}"] = z_vals
+        results[f"rgb_{typ}"] = out["rgb"]
+        results[f"depth_{typ}"] = out["depth"]
+        if fi:
+            results[f"rgb_instance_{typ}"] = out["rgb_instance"]
+            results[f"depth_instance_{typ}"] = out["depth_instance"]
+            results[f"opacity_instance_{typ}"] = out["opacity_instance"]
+        if keep:
+            saved[typ] = dict(z=z_vals, scene=scene, obj=obj, depth=out["depth"],
+                              noise_scene=engine._f32(ns) if ns is not None else None,
+                              noise_obj=engine._f32(no) if no is not None else None)
+
+    one_pass("coarse", z, 1)
+    if cfg["N_importance"] > 0:
+        z_fine = engine.sample_pdf_merge(z, results["weights_coarse"], cfg["N_importance"], det=(perturb == 0),
+                                         u=rand.get("u"), seed=seed + 2)
+        one_pass("fine", z_fine, 3)
+    return results, saved
+
+
 def render_rays(models: Dict[str, Any], embeddings: Dict[str, Any], rays: torch.Tensor, N_samples: int = 64,
                 use_disp: bool = False, perturb: float = 0, noise_std: float = 1, N_importance: int = 0,
                 chunk: int = 1024 * 32, white_back: bool = False, forward_instance: bool = True,
@@ -94,22 +143,40 @@ def render_rays(models: Dict[str, Any], embeddings: Dict[str, Any], rays: torch.
                 pass_through_mask: Optional[torch.Tensor] = None, rays_in_bbox: bool = False,
                 **dummy_kwargs):
     """Reference models/rendering.py:233-337: stratified sampling -> coarse pass -> importance resampling
-    -> fine pass.  rays (N,8) = [o, d, near, far]; returns the reference's result dict."""
-    rand = dummy_kwargs.get("_rand") or {}
+    -> fine pass.  rays (N,8) = [o, d, near, far]; returns the reference's result dict.  When parameters (or the
+    object codes) require grad under torch.enable_grad(), the result carries autograd through backward.py."""
     rays = rays.contiguous().float()
-    perturb = float(perturb)
-    seed = engine.new_seed() if (perturb > 0 or noise_std > 0) else 0
-    z = engine.sample_coarse(rays, N_samples, use_disp, perturb, rand.get("jitter"), seed)
-    results: Dict[str, Any] = {}
-    common = dict(embeddings=embeddings, chunk=chunk, noise_std=noise_std, white_back=white_back,
-                  forward_instance=forward_instance, embedding_instance=embedding_instance,
-                  frustum_bound_th=frustum_bound_th, pass_through_mask=pass_through_mask,
-                  rays_in_bbox=rays_in_bbox, _rays=rays, **dummy_kwargs)
-    inference_model(results=results, model=models["coarse"], typ="coarse", xyz=None, rays_d=None, z_vals=z,
-                    _seed=seed + 1, **common)
-    if N_importance > 0:
-        z_fine = engine.sample_pdf_merge(z, results["weights_coarse"], N_importance, det=(perturb == 0),
-                                         u=rand.get("u"), seed=seed + 2)
-        inference_model(results=results, model=models["fine"], typ="fine", xyz=None, rays_d=None, z_vals=z_fine,
-                        _seed=seed + 3, **common)
-    return results
+    emb_xyz = embeddings["xyz"]
+    cfg = dict(models=models, embeddings=embeddings, N_samples=N_samples, use_disp=use_disp, perturb=float(perturb),
+               noise_std=float(noise_std), N_importance=N_importance, white_back=white_back,
+               forward_instance=forward_instance, frustum_bound_th=float(frustum_bound_th),
+               pass_through_mask=pass_through_mask, rays_in_bbox=rays_in_bbox,
+               is_eval=bool(dummy_kwargs.get("is_eval", False)),
+               zero_last_delta=bool(dummy_kwargs.get("use_zero_as_last_delta", False)),
+               precision=dummy_kwargs.get("precision"), rand=dummy_kwargs.get("_rand") or {})
+    codes = embedding_instance
+    model_order = ["coarse"] + (["fine"] if N_importance > 0 else [])
+    trainable = [p for typ in model_order for p in models[typ].parameters()]
+    has_table = _is_voxel(emb_xyz)
+    needs_grad = torch.is_grad_enabled() and (
+        any(p.requires_grad for p in trainable) or (codes is not None and codes.requires_grad)
+        or (has_table and emb_xyz.embedding_space_ftr.weight.requires_grad))
+    if not needs_grad:
+        return _render_forward(cfg, rays, codes)[0]
+    if rays_in_bbox:
+        raise NotImplementedError("training with rays_in_bbox=True (weights swapped for sampling) is not built")
+    from . import backward
+    cfg["has_table"], cfg["model_order"] = has_table, model_order
+    params = ([emb_xyz.embedding_space_ftr.weight] if has_table else [])
+    for typ in model_order:
+        for w, b in engine.model_linears(models[typ]):
+            params += [w, b]
+    tensors = backward.RenderRaysFn.apply(cfg, rays, codes, *params)
+    keys = sorted(_result_keys(model_order, forward_instance))
+    return dict(zip(keys, tensors))
+
+
+def _result_keys(model_order, forward_instance):
+    base = ["weights", "opacity", "z_vals", "rgb", "depth"] + (
+        ["rgb_instance", "depth_instance", "opacity_instance"] if forward_instance else [])
+    return [f"{k}_{typ}" for typ in model_order for k in base]

@@ -282,11 +282,35 @@ def test_inference_model_call_surface(golden):
         close(res[k], gold[k], 5e-5, k)
 
 
-def test_grad_mode_fails_loudly():
-    from object_nerf_b200 import Embedding, render_rays
-    c = cases.RENDER_CASES["cfg1_plain"]
-    inp = cases.build_render_case(c)
-    model = helpers.make_model(inp["weights"]["coarse"], False, DEV).train()
-    with pytest.raises(NotImplementedError):
-        render_rays({"coarse": model}, {"xyz": Embedding(3, 10), "dir": Embedding(3, 4)}, inp["rays"].to(DEV),
-                    N_samples=64, perturb=0, noise_std=0, forward_instance=False)
+def test_training_step_gradients_match_reference_golden(golden):
+    """config 3 in miniature: render_rays (train mode) -> TotalLoss -> backward on the CUDA kernels, compared with
+    the REFERENCE's own backward (fixture written by tools/make_golden.py: loss, per-tensor norm + sampled entries)."""
+    from object_nerf_b200 import CodeLibrary, Embedding, render_rays
+    g = golden("grad_train_step")
+    c = cases.GRAD_CASE
+    inp = cases.build_grad_case()
+    models = {k: helpers.make_model(w, True, DEV).train() for k, w in inp["weights"].items()}
+    emb = helpers.GridModule(inp["grid"]).to(DEV)
+    lib = helpers.CodeLib(inp["code_table"]).to(DEV)
+    codes = lib.embedding_instance(inp["instance_ids"].view(-1).to(DEV))
+    rand = {k: v.to(DEV) for k, v in inp["rand"].items()}
+    out = render_rays(models, {"xyz": emb, "dir": Embedding(3, 4)}, inp["rays"].to(DEV), N_samples=c["n_samples"],
+                      perturb=c["perturb"], noise_std=c["noise_std"], N_importance=c["n_importance"],
+                      embedding_instance=codes, frustum_bound_th=c["frustum_bound_th"],
+                      pass_through_mask=inp["pass_through_mask"].to(DEV), is_eval=False, precision="fp32", _rand=rand)
+    batch = {k: v.to(DEV) for k, v in inp["batch"].items()}
+    loss = cases.total_loss(out, batch)
+    assert abs(loss.item() - g["loss"].item()) <= 2e-4 * abs(g["loss"].item()), (loss.item(), g["loss"].item())
+    loss.backward()
+    named = [(f"{typ}.{k}", p) for typ, m in models.items() for k, p in m.named_parameters()]
+    named += [("codes", lib.embedding_instance.weight), ("voxel", emb.embedding_space_ftr.weight)]
+    for name, p in named:
+        assert p.grad is not None, name
+        gr = p.grad.detach().cpu().reshape(-1)
+        ref_norm = g[name + "|norm"].item()
+        assert abs(gr.norm().item() - ref_norm) <= 2e-3 * max(ref_norm, 1e-7), (name, gr.norm().item(), ref_norm)
+        idx = cases.sample_indices(name, gr.numel())
+        err = (gr[idx] - g[name + "|samples"]).abs().max().item()
+        assert err <= 2e-3 * max(ref_norm, 1e-7) / max(1.0, gr.numel() ** 0.5) * 30 + 1e-7, (name, err, ref_norm)
+    nz = torch.nonzero(emb.embedding_space_ftr.weight.grad.abs().sum(1)).view(-1).cpu()
+    assert torch.equal(nz, g["voxel|nonzero_rows"])
