@@ -52,8 +52,8 @@ def inference_model(results: Dict[str, Any], model, embeddings: Dict[str, Any], 
     """Encode + two-branch MLP + compositing for one pass; fills `results` in place with the reference's
     keys (models/rendering.py:64-230).  `chunk` is accepted and ignored: the kernels tile internally."""
     if _needs_grad(model, embedding_instance):
-        raise NotImplementedError("backward of the fused render path is not built yet (SURVEY.md §8 row a14); "
-                                  "call under torch.no_grad()")
+        raise NotImplementedError("inference_model() is the no-grad call surface; gradients flow through "
+                                  "render_rays() (backward.RenderRaysFn)")
     n, s = z_vals.shape
     emb_xyz = embeddings["xyz"]
     use_voxel = _is_voxel(emb_xyz)

@@ -262,6 +262,55 @@ def test_render_rays_multi_matches_reference_golden(golden, name, precision):
             close(out[k], gold[k], 1e-4 if precision == "fp32" else 5e-2, k)
 
 
+def test_composite_backward_matches_oracle_autograd():
+    from object_nerf_b200 import backward as B
+    rng = np.random.default_rng(41)
+    n, s = 29, 96
+    rays = synth.random_rays(42, n)
+    z = O.merge_sorted(O.stratified_z(rays, 48), O.stratified_z(rays, 48) + 0.013)
+    f = lambda *sh: torch.from_numpy(rng.standard_normal(sh).astype(np.float32))
+    sigma, isigma = (f(n, s) * 5).requires_grad_(True), (f(n, s) * 5).requires_grad_(True)
+    rgb, irgb = torch.sigmoid(f(n, s, 3)).requires_grad_(True), torch.sigmoid(f(n, s, 3)).requires_grad_(True)
+    ns, no = f(n, s), f(n, s)
+    ptm = torch.from_numpy(rng.random((n, 1)) < 0.5)
+    ref = {}
+    O.composite_pass(ref, "x", sigma, rgb, isigma, irgb, z, noise_std=1.0, is_eval=False, frustum_bound_th=0.05,
+                     pass_through_mask=ptm, noise_scene=ns, noise_obj=no)
+    names = ["rgb", "depth", "opacity", "rgb_instance", "depth_instance", "opacity_instance"]
+    gout = {k: f(*ref[f"{k}_x"].shape) for k in names}
+    loss = sum((ref[f"{k}_x"] * gout[k]).sum() for k in names)
+    loss.backward()
+    scene = torch.cat([rgb, sigma[..., None]], -1).detach().contiguous().to(DEV)
+    obj = torch.cat([irgb, isigma[..., None]], -1).detach().contiguous().to(DEV)
+    dscene, dobj = B.composite_backward(z.to(DEV), scene, obj, ref["depth_x"].detach().to(DEV),
+                                        {k: v.to(DEV) for k, v in gout.items()}, 1.0, False, False, False, 0.05,
+                                        ptm.to(DEV), ns.to(DEV), no.to(DEV))
+    for got, want_rgb, want_sigma, nm in ((dscene, rgb.grad, sigma.grad, "scene"), (dobj, irgb.grad, isigma.grad, "obj")):
+        got = got.cpu()
+        scale = max(1.0, want_sigma.abs().max().item())
+        close(got[..., :3], want_rgb, 1e-5 * max(1.0, want_rgb.abs().max().item()), nm + " d_rgb")
+        close(got[..., 3], want_sigma, 2e-4 * scale, nm + " d_sigma")
+
+
+def test_gemm_kernel_all_modes():
+    import ctypes as C
+    from object_nerf_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(5)
+    for (M, N, K, ta) in ((70, 50, 33, 0), (3, 128, 5000, 1), (256, 271, 9000, 1), (200, 64, 1, 0), (1, 256, 4097, 1)):
+        A = torch.from_numpy(rng.standard_normal((K, M) if ta else (M, K)).astype(np.float32)).to(DEV)
+        Bm = torch.from_numpy(rng.standard_normal((K, N)).astype(np.float32)).to(DEV)
+        Cm = torch.ones(M, N, device=DEV)
+        want = (A.double().t() if ta else A.double()) @ Bm.double()
+        for acc in (0, 1):
+            Cm.fill_(1.0)
+            _lib.check(lib.onerf_gemm(_lib.ctx(torch.device(DEV, 0)), A.data_ptr(), A.shape[1], ta, Bm.data_ptr(), N,
+                                      Cm.data_ptr(), N, M, N, K, acc, _lib.stream()))
+            ref = want + (1.0 if acc else 0.0)
+            err = (Cm.double() - ref).abs().max().item()
+            assert err <= 1e-4 * max(1.0, ref.abs().max().item()), (M, N, K, ta, acc, err)
+
+
 def test_inference_model_call_surface(golden):
     """inference_model() with explicit xyz / rays_d, as the reference signature has it."""
     from object_nerf_b200 import Embedding, inference_model
@@ -311,6 +360,8 @@ def test_training_step_gradients_match_reference_golden(golden):
         assert abs(gr.norm().item() - ref_norm) <= 2e-3 * max(ref_norm, 1e-7), (name, gr.norm().item(), ref_norm)
         idx = cases.sample_indices(name, gr.numel())
         err = (gr[idx] - g[name + "|samples"]).abs().max().item()
-        assert err <= 2e-3 * max(ref_norm, 1e-7) / max(1.0, gr.numel() ** 0.5) * 30 + 1e-7, (name, err, ref_norm)
+        # per-entry: within 1 % of the tensor's RMS entry (fp32 accumulation order differs from torch's)
+        rms = max(ref_norm, 1e-7) / max(1.0, gr.numel() ** 0.5)
+        assert err <= 1e-2 * rms + 1e-8, (name, err, rms)
     nz = torch.nonzero(emb.embedding_space_ftr.weight.grad.abs().sum(1)).view(-1).cpu()
     assert torch.equal(nz, g["voxel|nonzero_rows"])
