@@ -12,7 +12,7 @@ models = {k: helpers.make_model(w, True, dev) for k, w in sc["weights"].items()}
 emb = helpers.GridModule(sc["grid"]).to(dev)
 n = 65536
 rays, codes = sc["rays"][:n].to(dev), sc["codes"][:n].to(dev)
-buf = torch.zeros(2048, dtype=torch.int64, device=dev)
+buf = torch.zeros(256, dtype=torch.int64, device=dev)
 lib = _lib.load()
 lib.onerf_debug_timeline.argtypes = [ctypes.c_void_p]
 with torch.no_grad():
@@ -28,17 +28,9 @@ t = buf.cpu().tolist()
 t0 = t[201]
 names = ["S0","S1","S2","S3","S4","S5","S6","S7","SFIN","SDIR","O0","O1","O2","O3","OFIN","ODIR"]
 print(f"encode: {t[200]-t0} cycles")
-print("epilogue (compute warp 0):  rank0 acc_ready_seen / arrive_done | rank1 acc_ready_seen / arrive_done")
+print("layer half | mma_first_issue  mma_last_commit | acc_ready_seen  epi_done | issue_span  ready->done(epi)  prev_done->issue")
+prev_done = t[200]
 for l in range(16):
     for h in range(2):
-        c0, d0 = t[(l*2+h)*4+2]-t0, t[(l*2+h)*4+3]-t0
-        c1, d1 = t[768+(l*2+h)*4+2]-t0, t[768+(l*2+h)*4+3]-t0
-        print(f"{names[l]:5s} h{h} | {c0:7d} {d0:7d} ({d0-c0:5d}) | {c1:7d} {d1:7d} ({d1-c1:5d})")
-print("MMA warp stages: start, after E/X waits (flags), after full wait, after issue")
-FL = {1:"H",2:"FIRST",4:"WX",8:"WE0",16:"WE1",32:"ACC",64:"h1"}
-for i in range(96):
-    if t[256+i*3]==0: break
-    a,b,c=[t[256+i*3+k]-t0 for k in range(3)]
-    e = t[640+i]//256 - t0; fl = t[640+i]%256
-    fs = "|".join(v for k,v in FL.items() if fl&k)
-    print(f"{i:3d}: start {a:7d}  Ewait {e-a:6d}  fullwait {b-e:6d}  issue {c-b:6d}   {fs}")
+        a, b, c, d = [t[(l*2+h)*4+k] - t0 for k in range(4)]
+        print(f"{names[l]:5s} h{h} | {a:8d} {b:8d} | {c:8d} {d:8d} | {b-a:6d} {d-c:6d} {c-b:6d}")
