@@ -26,6 +26,13 @@
 #include "encode.cuh"
 #include "field_common.cuh"
 
+// In-kernel clock64() timeline (tools/timeline.py): compiled in only with -DONERF_TIMELINE (make TIMELINE=1).
+#ifdef ONERF_TIMELINE
+#define ONERF_TL_ON true
+#else
+#define ONERF_TL_ON false
+#endif
+
 namespace {
 
 constexpr int TM = 128;             // samples per tile (UMMA M)
@@ -517,7 +524,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_tc_kernel(const __grid_c
             waited1 = true;
           }
           const uint32_t d_tmem = tmem_base + (uint32_t)(h * TM_ACC1);
-          if (P.timeline && blockIdx.x == 0 && tile == (int64_t)gridDim.x && lane == 0) P.timeline[(l * 2 + h) * 4 + 0] = clock64();
+          if (ONERF_TL_ON && P.timeline && blockIdx.x == 0 && tile == (int64_t)gridDim.x && lane == 0) P.timeline[(l * 2 + h) * 4 + 0] = clock64();
           for (int gi = 0; gi < Ly.ngroups; ++gi) {
             const int grp = Ly.groups[gi];
             const int first = grp & 31, cnt = (grp >> 5) & 7;
@@ -563,7 +570,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_tc_kernel(const __grid_c
               umma_commit(bar_empty + 8 * stage);
               if (gi == Ly.ngroups - 1) umma_commit(bar_acc_ready + 8 * h);
             }
-            if (gi == Ly.ngroups - 1 && P.timeline && blockIdx.x == 0 && tile == (int64_t)gridDim.x && lane == 0)
+            if (gi == Ly.ngroups - 1 && ONERF_TL_ON && P.timeline && blockIdx.x == 0 && tile == (int64_t)gridDim.x && lane == 0)
               P.timeline[(l * 2 + h) * 4 + 1] = clock64();
             __syncwarp();
             if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
@@ -583,7 +590,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_tc_kernel(const __grid_c
       mbar_arrive(bar_epi_done + 8);
     }
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      if (P.timeline && blockIdx.x == 0 && tile == (int64_t)gridDim.x && threadIdx.x == 0) P.timeline[201] = clock64();
+      if (ONERF_TL_ON && P.timeline && blockIdx.x == 0 && tile == (int64_t)gridDim.x && threadIdx.x == 0) P.timeline[201] = clock64();
       const int64_t e = tile * TM + row;
       const bool live = e < total;
       const int ray = live ? (int)(e / p.S) : 0;
@@ -628,7 +635,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_tc_kernel(const __grid_c
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_x_ready);
-      if (P.timeline && blockIdx.x == 0 && tile == (int64_t)gridDim.x && threadIdx.x == 0) P.timeline[200] = clock64();
+      if (ONERF_TL_ON && P.timeline && blockIdx.x == 0 && tile == (int64_t)gridDim.x && threadIdx.x == 0) P.timeline[200] = clock64();
 
       float sigma_part = 0.0f;
       for (int l = 0; l < P.n_layers; ++l) {
@@ -646,7 +653,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_tc_kernel(const __grid_c
           if (h == 0) { mbar_wait(bar_acc_ready, acc_phase0); acc_phase0 ^= 1; }
           else { mbar_wait(bar_acc_ready + 8, acc_phase1); acc_phase1 ^= 1; }
           tc_fence_after();
-          if (P.timeline && blockIdx.x == 0 && tile == (int64_t)gridDim.x && threadIdx.x == 0) P.timeline[(l * 2 + h) * 4 + 2] = clock64();
+          if (ONERF_TL_ON && P.timeline && blockIdx.x == 0 && tile == (int64_t)gridDim.x && threadIdx.x == 0) P.timeline[(l * 2 + h) * 4 + 2] = clock64();
           if (NC == 32) epilogue_half<32>(Ly, acc_addr, out_addr, bias_tab + l * 256, rc, headw, n, part0, part1, part2);
           else if (NC == 16) epilogue_half<16>(Ly, acc_addr, out_addr, bias_tab + l * 256, rc, headw, n, part0, part1, part2);
           else epilogue_half<8>(Ly, acc_addr, out_addr, bias_tab + l * 256, rc, headw, n, part0, part1, part2);
@@ -654,7 +661,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_tc_kernel(const __grid_c
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_epi_done + 8 * h);
-          if (P.timeline && blockIdx.x == 0 && tile == (int64_t)gridDim.x && threadIdx.x == 0) P.timeline[(l * 2 + h) * 4 + 3] = clock64();
+          if (ONERF_TL_ON && P.timeline && blockIdx.x == 0 && tile == (int64_t)gridDim.x && threadIdx.x == 0) P.timeline[(l * 2 + h) * 4 + 3] = clock64();
         }
         if (Ly.epi == EPI_HIDDEN_SIGMA) sigma_part = part0;
         if (Ly.epi == EPI_DIR) {
