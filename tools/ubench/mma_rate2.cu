@@ -8,7 +8,7 @@ __device__ __forceinline__ uint64_t mkdesc(uint32_t lo, uint32_t hi) { uint64_t 
 constexpr uint32_t HI128 = (1024u >> 4) | (1u << 14) | (2u << 29);
 constexpr uint32_t HI64 = (512u >> 4) | (1u << 14) | (4u << 29);
 
-template <int N, bool TS, int NMMA>
+template <int N, bool TS, int NMMA, int ALT>
 __global__ void __launch_bounds__(128, 1) k(long long* out) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint32_t slot;
@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(128, 1) k(long long* out) {
   __syncthreads();
   asm volatile("barrier.cluster.arrive.release.aligned;"); asm volatile("barrier.cluster.wait.acquire.aligned;");
   asm volatile("tcgen05.fence::after_thread_sync;");
-  const uint32_t tm = slot;
+  const uint32_t tm0 = slot; const uint32_t tm = tm0; (void)tm;
   if (threadIdx.x == 0 && rank == 0) {
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | (16u << 24);
     const uint32_t a_lo = ((base >> 4) & 0x3FFF) | 0x10000u;
@@ -36,8 +36,9 @@ __global__ void __launch_bounds__(128, 1) k(long long* out) {
 #pragma unroll
     for (int i = 0; i < NMMA; ++i) {
       const uint64_t db = mkdesc(b_lo + (uint32_t)((i & 15) * 2), HI64);
+      const uint32_t tm = tm0 + (ALT ? (uint32_t)(((i / ALT) & 1) * 256) : 0u);   // ALT: switch accumulator (and TMEM A) every ALT MMAs
       if (TS) asm volatile("{.reg .pred p; setp.eq.u32 p,1,1; tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;}" ::"r"(tm),
-                           "r"(tm + 256u + (uint32_t)((i & 15) * 8)), "l"(db), "r"(idesc));
+                           "r"(tm + 128u + (uint32_t)((i & 7) * 8)), "l"(db), "r"(idesc));
       else { const uint64_t da = mkdesc(a_lo + (uint32_t)((i & 3) * 2), HI128);
              asm volatile("{.reg .pred p; setp.eq.u32 p,1,1; tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;}" ::"r"(tm), "l"(da), "l"(db), "r"(idesc)); }
     }
@@ -53,11 +54,11 @@ __global__ void __launch_bounds__(128, 1) k(long long* out) {
   if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tm));
 }
 
-template <int N, bool TS>
+template <int N, bool TS, int ALT = 0>
 void run(const char* name) {
   constexpr int NMMA = 64;
   long long* d; cudaMalloc(&d, 16);
-  auto kern = k<N, TS, NMMA>;
+  auto kern = k<N, TS, NMMA, ALT>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaLaunchConfig_t cfg = {}; cfg.gridDim = dim3(2); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = 200 * 1024;
   cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -77,5 +78,9 @@ int main() {
   run<128, true>("2SM N=128 TS");
   run<64, true>("2SM N=64  TS");
   run<32, true>("2SM N=32  TS");
+  run<128, true, 4>("2SM N=128 TS alt-D every 4");
+  run<128, true, 1>("2SM N=128 TS alt-D every 1");
+  run<128, false, 4>("2SM N=128 SS alt-D every 4");
+  run<128, true, 16>("2SM N=128 TS alt-D every 16");
   return 0;
 }
