@@ -534,6 +534,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_tc_kernel(const __grid_c
             const int grp = Ly.groups[gi];
             const int first = grp & 31, cnt = (grp >> 5) & 7;
             const bool from_h = (grp >> 8) & 1;
+            // Descriptor words are formed BEFORE the barrier waits (the empty asm pins them there): whatever sits between
+            // a satisfied wait and the first tcgen05.mma is pure latency on the layer-to-layer dependency chain.
+            // High words are constants; the low words advance by (bytes >> 4) per K step.
+            const uint32_t b_lo0 = (((sB + stage * STAGE_BYTES) >> 4) & 0x3FFFu) | 0x10000u;
+            const uint32_t hb16 = half_bytes >> 4;
+            // X slabs: `first` is a multiple of 4, i.e. atom aligned; slab i2 sits at atom (i2 >> 1), half (i2 & 1)
+            const uint32_t a0 = from_h ? tmem_base + (uint32_t)(Ly.h_in_col + first * 16)
+                                       : ((((sX + (uint32_t)(first >> 1) * ATOM_BYTES) >> 4) & 0x3FFFu) | 0x10000u);
+            const uint32_t accum0 = (gi > 0) ? 1u : 0u;
+            asm volatile("" ::"r"(b_lo0), "r"(hb16), "r"(a0), "r"(accum0), "r"(d_tmem), "r"(idesc));
             if (((grp >> 9) & 1) && !waited1) {   // high-K half of the input activations
               mbar_wait(bar_epi_done + 8, ed_phase1);
               ed_phase1 ^= 1;
@@ -543,17 +553,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_tc_kernel(const __grid_c
             mbar_wait(bar_full + 8 * stage, phase);
             tc_fence_after();
             if (elect_one()) {
-              // Descriptors: the high words are constants, the low words advance by (bytes >> 4) per K step.
-              const uint32_t b_lo0 = (((sB + stage * STAGE_BYTES) >> 4) & 0x3FFFu) | 0x10000u;
-              const uint32_t hb16 = half_bytes >> 4;
-              uint32_t accum = (gi > 0) ? 1u : 0u;
+              uint32_t accum = accum0;
               if (!from_h) {
-                // X slabs: `first` is a multiple of 4, i.e. atom aligned; slab i2 sits at atom (i2 >> 1), half (i2 & 1)
-                const uint32_t a_lo0 = (((sX + (uint32_t)(first >> 1) * ATOM_BYTES) >> 4) & 0x3FFFu) | 0x10000u;
 #pragma unroll
                 for (int i2 = 0; i2 < STAGE_SLABS; ++i2) {
                   if (i2 < cnt) {
-                    const uint32_t a_lo = a_lo0 + (uint32_t)(i2 >> 1) * (ATOM_BYTES >> 4) + (uint32_t)(i2 & 1) * 4u;
+                    const uint32_t a_lo = a0 + (uint32_t)(i2 >> 1) * (ATOM_BYTES >> 4) + (uint32_t)(i2 & 1) * 4u;
                     const uint32_t b_lo = b_lo0 + (uint32_t)i2 * hb16;
                     umma_bf16(d_tmem, make_desc_hl(a_lo, DESC_HI_SW128), make_desc_hl(b_lo, DESC_HI_SW64), idesc, accum);
                     umma_bf16(d_tmem, make_desc_hl(a_lo + 2u, DESC_HI_SW128), make_desc_hl(b_lo + 2u, DESC_HI_SW64), idesc, 1u);
@@ -561,13 +566,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_tc_kernel(const __grid_c
                   }
                 }
               } else {
-                const uint32_t a_t0 = tmem_base + (uint32_t)(Ly.h_in_col + first * 16);
 #pragma unroll
                 for (int i2 = 0; i2 < STAGE_SLABS; ++i2) {
                   if (i2 < cnt) {
                     const uint32_t b_lo = b_lo0 + (uint32_t)i2 * hb16;
-                    umma_bf16_ts(d_tmem, a_t0 + (uint32_t)i2 * 16u, make_desc_hl(b_lo, DESC_HI_SW64), idesc, accum);
-                    umma_bf16_ts(d_tmem, a_t0 + (uint32_t)i2 * 16u + 8u, make_desc_hl(b_lo + 2u, DESC_HI_SW64), idesc, 1u);
+                    umma_bf16_ts(d_tmem, a0 + (uint32_t)i2 * 16u, make_desc_hl(b_lo, DESC_HI_SW64), idesc, accum);
+                    umma_bf16_ts(d_tmem, a0 + (uint32_t)i2 * 16u + 8u, make_desc_hl(b_lo + 2u, DESC_HI_SW64), idesc, 1u);
                     accum = 1u;
                   }
                 }
