@@ -167,6 +167,49 @@ typedef struct onerf_composite_args {
 int onerf_composite(onerf_ctx* ctx, const onerf_composite_args* args, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Whole forward of render_rays() in ONE call, models/rendering.py:233-337 (inference / validation: no autograd):
+ * stratified sampling -> coarse field + compositing -> importance resampling + merge -> fine field + compositing.
+ * It only enqueues the stage kernels above on `stream` (no host reads of device data, no allocation): the call is
+ * CUDA-graph capturable.  This is the function a non-Python host binds instead of models.rendering.render_rays.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct onerf_render_maps {   /* the reference's result dict for one pass ("coarse" / "fine"); all required */
+  float* weights;          /* (N,S) */
+  float* opacity;          /* (N,) */
+  float* z_vals;           /* (N,S): coarse = stratified depths, fine = merged sorted depths (S = n_samples + n_importance) */
+  float* rgb;              /* (N,3) */
+  float* depth;            /* (N,) */
+  float* rgb_instance;     /* (N,3)  } */
+  float* depth_instance;   /* (N,)   } required iff forward_instance */
+  float* opacity_instance; /* (N,)   } */
+} onerf_render_maps;
+
+typedef struct onerf_render_args {
+  const float* rays;            /* (N,8) = [o, d, near, far] */
+  const float* codes;           /* (N,64) object codes (embedding_instance), required iff forward_instance */
+  int n_rays, n_samples, n_importance;
+  const onerf_grid* grid;       /* NULL -> plain PE model */
+  const void* packed_coarse;    /* onerf_pack_weights of models["coarse"] */
+  const void* packed_fine;      /* ... of models["fine"]; required iff n_importance > 0 */
+  int precision;                /* onerf_precision */
+  int use_disp;
+  float perturb, noise_std;
+  uint64_t seed;                /* Philox seed of whatever random input is not given explicitly below */
+  const float* jitter;          /* (N, n_samples) U[0,1) or NULL */
+  const float* u;               /* (N, n_importance) U[0,1) or NULL (perturb == 0 -> deterministic linspace) */
+  const float* noise_scene_coarse, *noise_obj_coarse, *noise_scene_fine, *noise_obj_fine; /* (N,S) N(0,1) or NULL */
+  int white_back, forward_instance, is_eval, zero_last_delta, rays_in_bbox;
+  float frustum_bound_th;
+  const uint8_t* pass_through_mask; /* (N,) or NULL */
+  onerf_render_maps coarse;
+  onerf_render_maps fine;       /* written iff n_importance > 0 */
+  void* workspace;              /* >= onerf_render_rays_workspace_bytes(...) bytes, 256-byte aligned */
+  size_t workspace_bytes;
+} onerf_render_args;
+
+size_t onerf_render_rays_workspace_bytes(int n_rays, int n_samples, int n_importance);
+int onerf_render_rays_fwd(onerf_ctx* ctx, const onerf_render_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Backward building blocks (what loss.backward() does in the reference, train.py:180).
  * fp32.  object_nerf_b200/backward.py chains them into the gradient of render_rays.
  * ------------------------------------------------------------------------------------------- */

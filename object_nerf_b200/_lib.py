@@ -24,6 +24,7 @@ EXPORTS = [
     "onerf_abi_version", "onerf_last_error", "onerf_ctx_create", "onerf_ctx_destroy",
     "onerf_ctx_launch_count", "onerf_packed_weights_bytes", "onerf_pack_weights", "onerf_sample_coarse",
     "onerf_sample_pdf_merge", "onerf_sample_pdf", "onerf_encode", "onerf_field_fwd", "onerf_composite", "onerf_composite_multi",
+    "onerf_render_rays_workspace_bytes", "onerf_render_rays_fwd",
     "onerf_composite_bwd", "onerf_gemm", "onerf_leaky_bwd", "onerf_head_bwd", "onerf_segment_sum", "onerf_colsum",
     "onerf_dir_encode", "onerf_encode_bwd",
 ]
@@ -54,6 +55,24 @@ class CompositeArgs(C.Structure):
         ("frustum_bound_th", C.c_float), ("pass_through_mask", _p),
         ("weights", _p), ("opacity", _p), ("rgb", _p), ("depth", _p),
         ("rgb_instance", _p), ("depth_instance", _p), ("opacity_instance", _p),
+    ]
+
+
+class RenderMaps(C.Structure):
+    _fields_ = [("weights", _p), ("opacity", _p), ("z_vals", _p), ("rgb", _p), ("depth", _p),
+                ("rgb_instance", _p), ("depth_instance", _p), ("opacity_instance", _p)]
+
+
+class RenderArgs(C.Structure):
+    _fields_ = [
+        ("rays", _p), ("codes", _p), ("n_rays", C.c_int), ("n_samples", C.c_int), ("n_importance", C.c_int),
+        ("grid", C.POINTER(Grid)), ("packed_coarse", _p), ("packed_fine", _p), ("precision", C.c_int),
+        ("use_disp", C.c_int), ("perturb", C.c_float), ("noise_std", C.c_float), ("seed", C.c_uint64),
+        ("jitter", _p), ("u", _p), ("noise_scene_coarse", _p), ("noise_obj_coarse", _p), ("noise_scene_fine", _p),
+        ("noise_obj_fine", _p), ("white_back", C.c_int), ("forward_instance", C.c_int), ("is_eval", C.c_int),
+        ("zero_last_delta", C.c_int), ("rays_in_bbox", C.c_int), ("frustum_bound_th", C.c_float),
+        ("pass_through_mask", _p), ("coarse", RenderMaps), ("fine", RenderMaps), ("workspace", _p),
+        ("workspace_bytes", C.c_size_t),
     ]
 
 
@@ -98,6 +117,9 @@ def load() -> C.CDLL:
         lib.onerf_encode.argtypes = [_p, C.POINTER(Grid), _p, C.c_int64, _p, _p, _p]
         lib.onerf_field_fwd.argtypes = [_p, C.POINTER(FieldArgs), _p]
         lib.onerf_composite.argtypes = [_p, C.POINTER(CompositeArgs), _p]
+        lib.onerf_render_rays_workspace_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
+        lib.onerf_render_rays_workspace_bytes.restype = C.c_size_t
+        lib.onerf_render_rays_fwd.argtypes = [_p, C.POINTER(RenderArgs), _p]
         lib.onerf_composite_multi.argtypes = [_p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_int, _p, _p, _p, _p, _p, _p, _p, _p]
         lib.onerf_composite_bwd.argtypes = [_p, C.POINTER(CompositeArgs), _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]
         lib.onerf_gemm.argtypes = [_p, _p, C.c_int, C.c_int, _p, C.c_int, _p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _p]

@@ -90,3 +90,84 @@ extern "C" int onerf_field_fwd(onerf_ctx* ctx, const onerf_field_args* a, void* 
   onerf_set_error("onerf_field_fwd: unknown precision %d", a->precision);
   return ONERF_ERR_BAD_ARG;
 }
+
+// ------------------------------------------------------------------------------------------------
+// render_rays() forward as one call: composition of the stage entry points (same kernels, same order and seeds as
+// object_nerf_b200/rendering.py::_render_forward, so both routes give bit-identical results).
+// ------------------------------------------------------------------------------------------------
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+extern "C" size_t onerf_render_rays_workspace_bytes(int n_rays, int n_samples, int n_importance) {
+  if (n_rays < 0 || n_samples < 1 || n_importance < 0) return 0;
+  const size_t s_max = (size_t)n_samples + (size_t)n_importance;
+  return align256((size_t)n_rays * ONERF_RAY_CONST_FLOATS * sizeof(float)) +   // per-ray hoisted terms
+         2 * align256((size_t)n_rays * s_max * 4 * sizeof(float));             // (rgb, sigma) of both branches
+}
+
+static int render_pass(onerf_ctx* ctx, const onerf_render_args* a, const void* packed, const float* z, int S,
+                       const onerf_render_maps& m, const float* noise_scene, const float* noise_obj, uint64_t seed,
+                       float* ray_const, float* scene, float* obj, void* stream) {
+  onerf_field_args f;
+  memset(&f, 0, sizeof(f));
+  f.rays = a->rays; f.z = z; f.z_stride = S;
+  f.codes = a->forward_instance ? a->codes : nullptr;
+  f.n_rays = a->n_rays; f.n_samples = S;
+  f.grid = a->grid; f.packed = packed;
+  f.want_scene = 1; f.want_object = a->forward_instance ? 1 : 0;
+  f.precision = a->precision;
+  f.scene_out = scene; f.obj_out = a->forward_instance ? obj : nullptr; f.out_stride = S;
+  f.ray_const = ray_const;
+  int rc = onerf_field_fwd(ctx, &f, stream);
+  if (rc != ONERF_OK) return rc;
+  onerf_composite_args c;
+  memset(&c, 0, sizeof(c));
+  c.z = z; c.scene = scene; c.obj = a->forward_instance ? obj : nullptr;
+  c.n_rays = a->n_rays; c.n_samples = S;
+  c.noise_std = a->noise_std; c.noise_scene = noise_scene; c.noise_obj = noise_obj; c.seed = seed;
+  c.white_back = a->white_back; c.is_eval = a->is_eval; c.zero_last_delta = a->zero_last_delta;
+  c.rays_in_bbox = a->rays_in_bbox; c.frustum_bound_th = a->frustum_bound_th;
+  c.pass_through_mask = a->pass_through_mask;
+  c.weights = m.weights; c.opacity = m.opacity; c.rgb = m.rgb; c.depth = m.depth;
+  c.rgb_instance = m.rgb_instance; c.depth_instance = m.depth_instance; c.opacity_instance = m.opacity_instance;
+  return onerf_composite(ctx, &c, stream);
+}
+
+static bool maps_ok(const onerf_render_maps& m, int forward_instance) {
+  if (!(m.weights && m.opacity && m.z_vals && m.rgb && m.depth)) return false;
+  return !forward_instance || (m.rgb_instance && m.depth_instance && m.opacity_instance);
+}
+
+extern "C" int onerf_render_rays_fwd(onerf_ctx* ctx, const onerf_render_args* a, void* stream) {
+  ONERF_CHECK_ARG(ctx && a, "null argument");
+  ONERF_CHECK_ARG(a->rays && a->packed_coarse, "null rays / packed_coarse");
+  ONERF_CHECK_ARG(a->n_rays >= 0 && a->n_samples >= 2 && a->n_importance >= 0, "bad shape");
+  ONERF_CHECK_ARG(!a->forward_instance || a->codes, "forward_instance needs codes");
+  ONERF_CHECK_ARG(a->n_importance == 0 || a->packed_fine, "n_importance > 0 needs packed_fine");
+  ONERF_CHECK_ARG(maps_ok(a->coarse, a->forward_instance), "null coarse output map");
+  ONERF_CHECK_ARG(a->n_importance == 0 || maps_ok(a->fine, a->forward_instance), "null fine output map");
+  const size_t need = onerf_render_rays_workspace_bytes(a->n_rays, a->n_samples, a->n_importance);
+  ONERF_CHECK_ARG(a->workspace && (reinterpret_cast<uintptr_t>(a->workspace) & 255u) == 0, "workspace null or not 256-byte aligned");
+  if (a->workspace_bytes < need) {
+    onerf_set_error("onerf_render_rays_fwd: workspace too small (%zu < %zu)", a->workspace_bytes, need);
+    return ONERF_ERR_WORKSPACE;
+  }
+  if (a->n_rays == 0) return ONERF_OK;
+  const int S = a->n_samples, SF = a->n_samples + a->n_importance;
+  char* ws = reinterpret_cast<char*>(a->workspace);
+  float* ray_const = reinterpret_cast<float*>(ws);
+  ws += align256((size_t)a->n_rays * ONERF_RAY_CONST_FLOATS * sizeof(float));
+  float* scene = reinterpret_cast<float*>(ws);
+  ws += align256((size_t)a->n_rays * SF * 4 * sizeof(float));
+  float* obj = reinterpret_cast<float*>(ws);
+  // seeds: coarse depths, coarse noise, importance u, fine noise (rendering.py::_render_forward)
+  int rc = onerf_sample_coarse(ctx, a->rays, a->n_rays, S, a->use_disp, a->perturb, a->jitter, a->seed, a->coarse.z_vals, stream);
+  if (rc != ONERF_OK) return rc;
+  rc = render_pass(ctx, a, a->packed_coarse, a->coarse.z_vals, S, a->coarse, a->noise_scene_coarse, a->noise_obj_coarse,
+                   a->seed + 1, ray_const, scene, obj, stream);
+  if (rc != ONERF_OK || a->n_importance == 0) return rc;
+  rc = onerf_sample_pdf_merge(ctx, a->coarse.z_vals, a->coarse.weights, a->n_rays, S, a->n_importance, a->perturb == 0.0f ? 1 : 0,
+                              a->u, a->seed + 2, a->fine.z_vals, stream);
+  if (rc != ONERF_OK) return rc;
+  return render_pass(ctx, a, a->packed_fine, a->fine.z_vals, SF, a->fine, a->noise_scene_fine, a->noise_obj_fine, a->seed + 3,
+                     ray_const, scene, obj, stream);
+}

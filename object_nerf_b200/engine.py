@@ -280,3 +280,65 @@ def composite_multi(z_all, field_all, white_back=False, want_ids=False, want_uns
     if want_unsorted:
         out["weights_unsorted"] = unsorted
     return out
+
+
+class RenderPlan:
+    """Buffers + argument block of one onerf_render_rays_fwd() call (the whole forward of render_rays in ONE C call,
+    models/rendering.py:233-337 without autograd).  All outputs and the workspace are allocated once, so `run()` only
+    enqueues kernels: it can be captured in a CUDA graph and replayed."""
+
+    MAP_KEYS = ("weights", "opacity", "z_vals", "rgb", "depth", "rgb_instance", "depth_instance", "opacity_instance")
+
+    def __init__(self, rays, packed_coarse, packed_fine, grid: Optional[GridBuffers], codes=None, n_samples=64,
+                 n_importance=0, use_disp=False, perturb=0.0, noise_std=0.0, white_back=False, forward_instance=True,
+                 is_eval=False, zero_last_delta=False, rays_in_bbox=False, frustum_bound_th=0.0,
+                 pass_through_mask=None, precision=None, seed=0, rand=None):
+        lib = _lib.load()
+        self.rays = _f32(rays)
+        n, dev = self.rays.shape[0], self.rays.device
+        rand = rand or {}
+        self._keep = [self.rays, packed_coarse, packed_fine, grid]
+        f = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=dev)
+        self.maps = {}
+        a = _lib.RenderArgs()
+        for typ, s in (("coarse", n_samples), ("fine", n_samples + n_importance)):
+            if typ == "fine" and n_importance == 0:
+                continue
+            m = dict(weights=f(n, s), opacity=f(n), z_vals=f(n, s), rgb=f(n, 3), depth=f(n))
+            if forward_instance:
+                m.update(rgb_instance=f(n, 3), depth_instance=f(n), opacity_instance=f(n))
+            self.maps[typ] = m
+            cm = getattr(a, typ)
+            for k, v in m.items():
+                setattr(cm, k, v.data_ptr())
+        ws_bytes = lib.onerf_render_rays_workspace_bytes(n, n_samples, n_importance)
+        self.workspace = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=dev)
+        assert self.workspace.data_ptr() % 256 == 0
+        codes = _f32(codes) if (codes is not None and forward_instance) else None
+        mask = None
+        if pass_through_mask is not None:
+            mask = pass_through_mask.reshape(-1).to(torch.uint8).contiguous()
+        opt = {k: (_f32(rand[k]) if rand.get(k) is not None else None)
+               for k in ("jitter", "u", "noise_scene_coarse", "noise_obj_coarse", "noise_scene_fine", "noise_obj_fine")}
+        self._keep += [codes, mask, opt]
+        a.rays, a.codes = self.rays.data_ptr(), _lib.ptr(codes)
+        a.n_rays, a.n_samples, a.n_importance = n, n_samples, n_importance
+        a.grid = C.pointer(grid.c) if grid is not None else None
+        a.packed_coarse = packed_coarse.data_ptr()
+        a.packed_fine = packed_fine.data_ptr() if packed_fine is not None else None
+        a.precision = PRECISIONS[precision or default_precision()]
+        a.use_disp, a.perturb, a.noise_std, a.seed = int(use_disp), float(perturb), float(noise_std), seed
+        a.jitter, a.u = _lib.ptr(opt["jitter"]), _lib.ptr(opt["u"])
+        a.noise_scene_coarse, a.noise_obj_coarse = _lib.ptr(opt["noise_scene_coarse"]), _lib.ptr(opt["noise_obj_coarse"])
+        a.noise_scene_fine, a.noise_obj_fine = _lib.ptr(opt["noise_scene_fine"]), _lib.ptr(opt["noise_obj_fine"])
+        a.white_back, a.forward_instance, a.is_eval = int(white_back), int(forward_instance), int(is_eval)
+        a.zero_last_delta, a.rays_in_bbox = int(zero_last_delta), int(rays_in_bbox)
+        a.frustum_bound_th = float(frustum_bound_th)
+        a.pass_through_mask = _lib.ptr(mask)
+        a.workspace, a.workspace_bytes = self.workspace.data_ptr(), self.workspace.numel()
+        self.args = a
+
+    def run(self):
+        """Enqueue the forward on the current stream; returns the reference's result dict (views of the plan's buffers)."""
+        _lib.check(_lib.load().onerf_render_rays_fwd(_lib.ctx(self.rays.device), C.byref(self.args), _lib.stream()))
+        return {f"{k}_{typ}": v for typ, m in self.maps.items() for k, v in m.items()}

@@ -180,6 +180,68 @@ def _run_render_case(c, precision):
                            precision=precision, _rand=rand)
 
 
+
+def _plan_for_case(c, precision):
+    """The same case through the ONE-CALL C entry point onerf_render_rays_fwd (engine.RenderPlan)."""
+    from object_nerf_b200 import engine
+    from object_nerf_b200.rendering import _grid_of, _is_voxel
+    from object_nerf_b200 import Embedding
+    inp = cases.build_render_case(c)
+    uv = c["use_voxel"]
+    models = {"coarse": helpers.make_model(inp["weights"]["coarse"], uv, DEV)}
+    if c["n_importance"] > 0:
+        models["fine"] = helpers.make_model(inp["weights"]["fine"], uv, DEV)
+    emb = helpers.GridModule(inp["grid"]).to(DEV) if uv else Embedding(3, 10)
+    assert _is_voxel(emb) == uv
+    rand = {k: v.to(DEV) for k, v in inp["rand"].items()}
+    ptm = inp["pass_through_mask"].to(DEV) if inp["pass_through_mask"] is not None else None
+    return engine.RenderPlan(
+        inp["rays"].to(DEV), engine.packed_for(models["coarse"], uv),
+        engine.packed_for(models["fine"], uv) if c["n_importance"] > 0 else None, _grid_of(emb),
+        codes=inp["codes"].to(DEV), n_samples=c["n_samples"], n_importance=c["n_importance"], use_disp=c["use_disp"],
+        perturb=c["perturb"], noise_std=c["noise_std"], white_back=c["white_back"],
+        forward_instance=c["forward_instance"], is_eval=c["is_eval"], rays_in_bbox=c["rays_in_bbox"],
+        frustum_bound_th=c["frustum_bound_th"], pass_through_mask=ptm, precision=precision, rand=rand), models, emb
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("name", list(cases.RENDER_CASES))
+def test_one_call_render_entry_is_bit_identical_to_the_staged_path(name, precision):
+    """onerf_render_rays_fwd (one C call, what a non-Python host binds) runs the same kernels in the same order as the
+    Python-orchestrated render_rays(): every output map must be bit-identical."""
+    c = cases.RENDER_CASES[name]
+    staged = _run_render_case(c, precision)
+    plan, _models, _emb = _plan_for_case(c, precision)
+    fused = plan.run()
+    torch.cuda.synchronize()
+    assert set(fused) == set(staged)
+    for k in staged:
+        assert torch.equal(fused[k], staged[k]), k
+
+
+def test_one_call_render_entry_is_cuda_graph_capturable():
+    """no host reads of device data, no allocation on the hot path -> the whole forward captures into a
+    CUDA graph; replays reproduce the eager result bit for bit."""
+    c = cases.RENDER_CASES["eval_voxel"]
+    plan, _models, _emb = _plan_for_case(c, "bf16")
+    eager = {k: v.clone() for k, v in plan.run().items()}
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        plan.run()                                   # warm-up on the capture stream
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            out = plan.run()
+    torch.cuda.current_stream().wait_stream(side)
+    for _ in range(2):
+        for v in out.values():
+            v.zero_()
+        g.replay()
+        torch.cuda.synchronize()
+        for k in eager:
+            assert torch.equal(out[k], eager[k]), k
+
 @pytest.mark.parametrize("precision", PRECISIONS)
 @pytest.mark.parametrize("name", list(cases.RENDER_CASES))
 def test_render_rays_matches_reference_golden(golden, name, precision):
