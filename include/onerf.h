@@ -210,6 +210,43 @@ size_t onerf_render_rays_workspace_bytes(int n_rays, int n_samples, int n_import
 int onerf_render_rays_fwd(onerf_ctx* ctx, const onerf_render_args* args, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Rays: the two host steps directly in front of the path, on the device.
+ * `_host` pointers are read on the host at call time (a 3x4 pose, one box), everything else is device memory.
+ * ------------------------------------------------------------------------------------------- */
+
+/* get_ray_directions, datasets/ray_utils.py:5-25: directions (H,W,3), pixel (row y, column x) ->
+ * ((x - W/2) / focal, -(y - H/2) / focal, -1); no +0.5 pixel centring. */
+int onerf_ray_directions(onerf_ctx* ctx, int H, int W, float focal, float* directions, void* stream);
+
+/* get_rays, datasets/ray_utils.py:28-51: rays_d = normalise(directions @ c2w[:, :3]^T), rays_o = c2w[:, 3];
+ * directions (n,3), c2w_host 12 floats row-major (3,4), outputs (n,3). */
+int onerf_get_rays(onerf_ctx* ctx, const float* directions, int64_t n, const float* c2w_host, float* rays_o, float* rays_d,
+                   void* stream);
+
+/* One object's box as BBoxRayHelper holds it (utils/bbox_utils.py): pose_avg and axis_align_mat as row-major 4x4
+ * (or 3x4: only the first 12 entries are read), bounds = [lo(3), hi(3)] with any bbox_enlarge already applied
+ * (utils/bbox_utils.py:140-145). */
+typedef struct onerf_box_host {
+  double pose_avg[16];
+  double axis_align[16];
+  double bounds[6];
+} onerf_box_host;
+
+/* generate_rays, render_tools/editable_renderer.py:153-181: (n,8) rays = [o, d, near, far] of one object.
+ * box == NULL (obj_id 0): near / far = the constants near / scale_factor, far / scale_factor.  Otherwise the ray is
+ * taken to the box frame (utils/bbox_utils.py:102-117: fp32 unscale, float64 rigid transforms, direction rotated by the
+ * axis-alignment matrix only) and slab-tested in float64 (datasets/geo_utils.py:126-162: zero direction components
+ * -> 1e-14, origin inside the box -> miss); near / far = hit distances / scale_factor, 0 / 0 for a miss.
+ * hit_out (n,) u8 or NULL = the bbox mask. */
+int onerf_generate_rays(onerf_ctx* ctx, const float* rays_o, const float* rays_d, int64_t n, const onerf_box_host* box_host,
+                        double scale_factor, double near, double far, float* rays_out, uint8_t* hit_out, void* stream);
+
+/* The three steps fused: pixel grid + pose (+ box) -> (H*W,8) rays in one kernel; the renderer then needs only
+ * (H, W, focal, pose) per object instead of host-built ray tensors. */
+int onerf_camera_rays(onerf_ctx* ctx, int H, int W, float focal, const float* c2w_host, const onerf_box_host* box_host,
+                      double scale_factor, double near, double far, float* rays_out, uint8_t* hit_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Backward building blocks (what loss.backward() does in the reference, train.py:180).
  * fp32.  object_nerf_b200/backward.py chains them into the gradient of render_rays.
  * ------------------------------------------------------------------------------------------- */

@@ -25,6 +25,7 @@ EXPORTS = [
     "onerf_ctx_launch_count", "onerf_packed_weights_bytes", "onerf_pack_weights", "onerf_sample_coarse",
     "onerf_sample_pdf_merge", "onerf_sample_pdf", "onerf_encode", "onerf_field_fwd", "onerf_composite", "onerf_composite_multi",
     "onerf_render_rays_workspace_bytes", "onerf_render_rays_fwd",
+    "onerf_ray_directions", "onerf_get_rays", "onerf_generate_rays", "onerf_camera_rays",
     "onerf_composite_bwd", "onerf_gemm", "onerf_leaky_bwd", "onerf_head_bwd", "onerf_segment_sum", "onerf_colsum",
     "onerf_dir_encode", "onerf_encode_bwd",
 ]
@@ -56,6 +57,10 @@ class CompositeArgs(C.Structure):
         ("weights", _p), ("opacity", _p), ("rgb", _p), ("depth", _p),
         ("rgb_instance", _p), ("depth_instance", _p), ("opacity_instance", _p),
     ]
+
+
+class BoxHost(C.Structure):
+    _fields_ = [("pose_avg", C.c_double * 16), ("axis_align", C.c_double * 16), ("bounds", C.c_double * 6)]
 
 
 class RenderMaps(C.Structure):
@@ -120,6 +125,11 @@ def load() -> C.CDLL:
         lib.onerf_render_rays_workspace_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
         lib.onerf_render_rays_workspace_bytes.restype = C.c_size_t
         lib.onerf_render_rays_fwd.argtypes = [_p, C.POINTER(RenderArgs), _p]
+        lib.onerf_ray_directions.argtypes = [_p, C.c_int, C.c_int, C.c_float, _p, _p]
+        lib.onerf_get_rays.argtypes = [_p, _p, C.c_int64, C.POINTER(C.c_float), _p, _p, _p]
+        lib.onerf_generate_rays.argtypes = [_p, _p, _p, C.c_int64, C.POINTER(BoxHost), C.c_double, C.c_double, C.c_double, _p, _p, _p]
+        lib.onerf_camera_rays.argtypes = [_p, C.c_int, C.c_int, C.c_float, C.POINTER(C.c_float), C.POINTER(BoxHost), C.c_double,
+                                          C.c_double, C.c_double, _p, _p, _p]
         lib.onerf_composite_multi.argtypes = [_p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_int, _p, _p, _p, _p, _p, _p, _p, _p]
         lib.onerf_composite_bwd.argtypes = [_p, C.POINTER(CompositeArgs), _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]
         lib.onerf_gemm.argtypes = [_p, _p, C.c_int, C.c_int, _p, C.c_int, _p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _p]

@@ -412,3 +412,91 @@ def render_rays_multi(weights, grid, code_table, rays_list, obj_instance_ids, n_
         rgbs, sigmas = eval_all("fine", z_fine)
         composite_multi(out, "fine", z_fine, rgbs, sigmas, white_back)
     return out
+
+
+# --------------------------------------------------------------------------------------------
+# rays: camera ray generation and per-object ray assembly
+# --------------------------------------------------------------------------------------------
+def ray_directions(H: int, W: int, focal: float) -> torch.Tensor:
+    """datasets/ray_utils.py:5-25 (get_ray_directions).  kornia.create_meshgrid(H, W, normalized_coordinates=False)[0]
+    is grid[y, x] = (x, y) with x = linspace(0, W-1, W), y = linspace(0, H-1, H) (kornia is not installed here: its
+    published semantics are restated).  No +0.5 pixel centring (:19-20).  Returns (H, W, 3) fp32."""
+    xs = torch.linspace(0, W - 1, W)
+    ys = torch.linspace(0, H - 1, H)
+    i = xs[None, :].expand(H, W)
+    j = ys[:, None].expand(H, W)
+    return torch.stack([(i - W / 2) / focal, -(j - H / 2) / focal, -torch.ones_like(i)], -1)
+
+
+def get_rays(directions: torch.Tensor, c2w: torch.Tensor):
+    """datasets/ray_utils.py:28-51: rotate by c2w[:, :3], normalise, origin = c2w[:, 3]; returns (H*W, 3) each."""
+    rays_d = directions @ c2w[:, :3].T
+    rays_d = rays_d / torch.norm(rays_d, dim=-1, keepdim=True)
+    rays_o = c2w[:, 3].expand(rays_d.shape)
+    return rays_o.reshape(-1, 3), rays_d.reshape(-1, 3)
+
+
+def bbox_intersection(bounds, orig, dirn):
+    """datasets/geo_utils.py:126-162 (slab test, float64): zero direction components become 1e-14 (:131), a ray whose
+    origin is inside the box (tmin < 0 or tmax < 0) is a MISS (:158-160).  bounds (2,3); returns (hit, near, far)."""
+    import numpy as np
+    dirn = np.array(dirn, dtype=np.float64)
+    dirn[dirn == 0] = 1.0e-14
+    invdir = 1 / dirn
+    sign = (invdir < 0).astype(np.int64)
+    tmin = (bounds[sign[0]][0] - orig[0]) * invdir[0]
+    tmax = (bounds[1 - sign[0]][0] - orig[0]) * invdir[0]
+    tymin = (bounds[sign[1]][1] - orig[1]) * invdir[1]
+    tymax = (bounds[1 - sign[1]][1] - orig[1]) * invdir[1]
+    if tmin > tymax or tymin > tmax:
+        return False, 0.0, 0.0
+    tmin, tmax = max(tmin, tymin), min(tmax, tymax)
+    tzmin = (bounds[sign[2]][2] - orig[2]) * invdir[2]
+    tzmax = (bounds[1 - sign[2]][2] - orig[2]) * invdir[2]
+    if tmin > tzmax or tzmin > tmax:
+        return False, 0.0, 0.0
+    tmin, tmax = max(tmin, tzmin), min(tmax, tzmax)
+    if tmin < 0 or tmax < 0:
+        return False, 0.0, 0.0
+    return True, tmin, tmax
+
+
+def ray_bbox_intersections(rays_o, rays_d, pose_avg, axis_align_mat, bbox_bounds, scale_factor, bbox_enlarge=0.0):
+    """utils/bbox_utils.py:102-156: rays (fp32, NeRF scale) -> box frame -> slab test.  The unscale is an fp32 multiply
+    (:109), the two rigid transforms are float64 (:111-116); the direction is rotated by the axis-alignment matrix ONLY
+    (:116 uses rays_d, not the de-centred direction - kept).  Returns (mask bool (N,), near (N,1), far (N,1)) with
+    near / far = fp32(t) / scale_factor (:151-155)."""
+    import numpy as np
+    o = rays_o.detach().cpu().numpy() * scale_factor
+    d = rays_d.detach().cpu().numpy()
+    Ta = np.asarray(pose_avg, dtype=np.float64).squeeze()
+    Tb = np.asarray(axis_align_mat, dtype=np.float64)
+    o_box = (Ta[:3, :3] @ o.T).T + Ta[:3, 3]
+    o_box = (Tb[:3, :3] @ o_box.T).T + Tb[:3, 3]
+    d_box = (Tb[:3, :3] @ d.T).T
+    bounds = np.array(bbox_bounds, dtype=np.float64, copy=True)
+    if bbox_enlarge > 0:
+        bounds[0] -= bbox_enlarge
+        bounds[1] += bbox_enlarge
+    n = o.shape[0]
+    hit, near, far = np.empty(n), np.empty(n), np.empty(n)
+    for k in range(n):
+        hit[k], near[k], far[k] = bbox_intersection(bounds, o_box[k], d_box[k])
+    mask = torch.Tensor(hit).bool()
+    near_t, far_t = torch.Tensor(near[..., None]), torch.Tensor(far[..., None])
+    return mask, near_t / scale_factor, far_t / scale_factor
+
+
+def generate_rays(obj_id, rays_o, rays_d, near, far, scale_factor, box=None, bbox_enlarge=0.0):
+    """render_tools/editable_renderer.py:153-181: (N,8) rays of one object.  Scene (obj_id == 0): constant near / far
+    divided by the scale factor; objects: box hit distances, 0 / 0 for rays that miss (:173-176).
+    box = dict(pose_avg, axis_align_mat, bbox_bounds)."""
+    if obj_id == 0:
+        batch_near = near / scale_factor * torch.ones_like(rays_o[:, :1])
+        batch_far = far / scale_factor * torch.ones_like(rays_o[:, :1])
+        return torch.cat([rays_o, rays_d, batch_near, batch_far], 1)
+    mask, bn, bf = ray_bbox_intersections(rays_o, rays_d, box["pose_avg"], box["axis_align_mat"], box["bbox_bounds"],
+                                          scale_factor, bbox_enlarge)
+    bn[~mask] = 0
+    bf[~mask] = 0
+    return torch.cat([rays_o, rays_d, bn, bf], 1)

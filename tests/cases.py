@@ -195,3 +195,72 @@ def sample_indices(name, numel):
     import zlib
     rng = np.random.default_rng(zlib.crc32(name.encode()))
     return torch.from_numpy(rng.integers(0, numel, size=min(GRAD_SAMPLES, numel)))
+
+
+# ------------------------------------------------------------------------------------------------
+# camera rays / per-object ray assembly
+# ------------------------------------------------------------------------------------------------
+CAMERA_CASES = {
+    "cam_small": dict(H=24, W=32, fovx_deg=70.0, seed=301),
+    "cam_odd": dict(H=37, W=53, fovx_deg=55.0, seed=302),
+}
+
+
+def build_camera_case(c):
+    """focal as editable_renderer.py:190, a random rigid camera-to-world pose (3,4) fp32."""
+    import numpy as np
+    rng = np.random.Generator(np.random.PCG64(c["seed"]))
+    focal = (c["W"] / 2) / np.tan((c["fovx_deg"] / 2) / (180 / np.pi))
+    q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+    if np.linalg.det(q) < 0:
+        q[:, 0] = -q[:, 0]
+    t = rng.uniform(-1.0, 1.0, size=3)
+    c2w = torch.from_numpy(np.concatenate([q, t[:, None]], 1).astype(np.float32))
+    return dict(H=c["H"], W=c["W"], focal=float(focal), c2w=c2w)
+
+
+BBOX_CASES = {
+    "bbox_basic": dict(n_rays=4096, enlarge=0.0, scale=2.0, seed=311),
+    "bbox_enlarged": dict(n_rays=2048, enlarge=0.07, scale=16.0, seed=312),
+}
+
+
+def build_bbox_case(c):
+    """Rays around a box given in a rotated / translated frame: most aimed at the box, some missing it, some starting
+    INSIDE it (a miss by the reference's rule), some with exactly-zero direction components (the 1e-14 rule)."""
+    import numpy as np
+    rng = np.random.Generator(np.random.PCG64(c["seed"]))
+    n, s = c["n_rays"], c["scale"]
+
+    def rigid(rotate):
+        q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+        if np.linalg.det(q) < 0:
+            q[:, 0] = -q[:, 0]
+        T = np.eye(4)
+        if rotate:
+            T[:3, :3] = q
+        T[:3, 3] = rng.uniform(-0.5, 0.5, size=3)
+        return T
+
+    # pose_avg is a pure translation, as in the datasets: the reference rotates the DIRECTION by the axis-alignment
+    # matrix only (utils/bbox_utils.py:116), which is consistent only then (SURVEY appendix A.13)
+    pose_avg, axis = rigid(False), rigid(True)
+    lo = np.array([-0.6, -0.4, -0.3]) + rng.uniform(-0.05, 0.05, 3)
+    hi = np.array([0.5, 0.7, 0.4]) + rng.uniform(-0.05, 0.05, 3)
+    bounds = np.stack([lo, hi])
+    # choose world-space (NeRF scale) origins / targets by mapping box-frame points back
+    Tinv = np.linalg.inv(axis @ pose_avg)
+    def to_world(pb):
+        return ((Tinv[:3, :3] @ pb.T).T + Tinv[:3, 3]) / s
+    centre, half = (lo + hi) / 2, (hi - lo) / 2
+    tgt_box = centre + rng.uniform(-1.4, 1.4, size=(n, 3)) * half          # ~50 % inside the box footprint
+    org_box = centre + rng.normal(size=(n, 3)) * 3.0
+    inside = rng.uniform(size=n) < 0.1
+    org_box[inside] = centre + rng.uniform(-0.9, 0.9, size=(int(inside.sum()), 3)) * half
+    o = to_world(org_box).astype(np.float32)
+    d = to_world(tgt_box) - to_world(org_box)
+    d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    zero = rng.uniform(size=n) < 0.05
+    d[zero, rng.integers(0, 3, size=int(zero.sum()))] = 0.0
+    return dict(rays_o=torch.from_numpy(o), rays_d=torch.from_numpy(d), pose_avg=pose_avg, axis_align_mat=axis,
+                bbox_bounds=bounds, scale_factor=float(s), bbox_enlarge=float(c["enlarge"]), near=0.3, far=6.0)

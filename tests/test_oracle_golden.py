@@ -127,3 +127,29 @@ def test_training_step_gradients_match_reference(golden):
 def helpers_name(k):
     from tests.helpers import REF_NAMES
     return REF_NAMES[k]
+
+
+# ------------------------------------------------------------------------------------------------
+# camera rays / per-object ray assembly
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", list(cases.CAMERA_CASES))
+def test_camera_rays_match_reference_golden(golden, name):
+    inp = cases.build_camera_case(cases.CAMERA_CASES[name])
+    gold = golden("rays_" + name)
+    directions = O.ray_directions(inp["H"], inp["W"], inp["focal"])
+    assert torch.equal(directions, gold["directions"])
+    rays_o, rays_d = O.get_rays(directions, inp["c2w"])
+    assert torch.equal(rays_o, gold["rays_o"]) and torch.equal(rays_d, gold["rays_d"])
+
+
+@pytest.mark.parametrize("name", list(cases.BBOX_CASES))
+def test_ray_bbox_intersections_match_reference_golden(golden, name):
+    inp = cases.build_bbox_case(cases.BBOX_CASES[name])
+    gold = golden("rays_" + name)
+    mask, near, far = O.ray_bbox_intersections(inp["rays_o"], inp["rays_d"], inp["pose_avg"], inp["axis_align_mat"],
+                                               inp["bbox_bounds"], inp["scale_factor"], inp["bbox_enlarge"])
+    assert torch.equal(mask, gold["mask"].bool())
+    assert torch.equal(near, gold["near"]) and torch.equal(far, gold["far"])
+    # the cases exercise every rule of the slab test
+    d = inp["rays_d"]
+    assert (d == 0).any() and mask.any() and (~mask).any()

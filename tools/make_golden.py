@@ -239,8 +239,32 @@ def gen_gridbuild():
          voxel_size=emb.voxel_size)
 
 
+def gen_ray_cases():
+    """the reference's own get_ray_directions / get_rays (datasets/ray_utils.py) and
+    BBoxRayHelper.get_ray_bbox_intersections (utils/bbox_utils.py:132-156, numba slab test of datasets/geo_utils.py).
+    The helper's constructor parses dataset files, so an instance is made without it and given the three attributes
+    the method reads."""
+    from datasets.ray_utils import get_ray_directions, get_rays
+    from utils.bbox_utils import BBoxRayHelper
+    for name, c in cases.CAMERA_CASES.items():
+        inp = cases.build_camera_case(c)
+        directions = get_ray_directions(inp["H"], inp["W"], inp["focal"])
+        rays_o, rays_d = get_rays(directions, inp["c2w"])
+        save("rays_" + name, directions=directions, rays_o=rays_o.contiguous(), rays_d=rays_d)
+    for name, c in cases.BBOX_CASES.items():
+        inp = cases.build_bbox_case(c)
+        h = object.__new__(BBoxRayHelper)
+        h.pose_avg, h.axis_align_mat, h.bbox_bounds = inp["pose_avg"], inp["axis_align_mat"], inp["bbox_bounds"]
+        h.scale_factor = inp["scale_factor"]
+        mask, near, far = h.get_ray_bbox_intersections(inp["rays_o"], inp["rays_d"], inp["scale_factor"],
+                                                       bbox_enlarge=inp["bbox_enlarge"])
+        save("rays_" + name, mask=mask, near=near, far=far)
+        print(name, "hits", int(mask.sum()), "of", mask.numel())
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    gen_ray_cases()
     gen_gridbuild()
     gen_grad_case()
     gen_stage_cases()

@@ -51,7 +51,16 @@ def install():
                  "imageio", "mcubes"):
         _stub(name)
     k = _stub("kornia")
-    k.create_meshgrid = None  # datasets/ray_utils.py:2 imports it at module scope; never called here
+    def create_meshgrid(height, width, normalized_coordinates=True, device=None, dtype=None):
+        """kornia is not installed: its published create_meshgrid restated (1 x H x W x 2, last dim = (x, y))."""
+        xs = torch.linspace(0, width - 1, width)
+        ys = torch.linspace(0, height - 1, height)
+        if normalized_coordinates:
+            xs = (xs / (width - 1) - 0.5) * 2
+            ys = (ys / (height - 1) - 0.5) * 2
+        base = torch.stack(torch.meshgrid([xs, ys], indexing="ij"), dim=-1)
+        return base.permute(1, 0, 2).unsqueeze(0)
+    k.create_meshgrid = create_meshgrid  # datasets/ray_utils.py:2,17
     o3d = _stub("open3d")
     io = _stub("open3d.io")
     io.read_point_cloud = lambda p: _FakePcd(_PCD_REGISTRY[p])
