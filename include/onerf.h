@@ -247,6 +247,44 @@ int onerf_camera_rays(onerf_ctx* ctx, int H, int W, float focal, const float* c2
                       double scale_factor, double near, double far, float* rays_out, uint8_t* hit_out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Training loss: TotalLoss, models/losses.py:5-135, and d(loss_sum)/d(map) for the ten
+ * rendered maps, without host synchronisation.  Five masked-MSE terms, each summed over the coarse (and fine) maps:
+ *   color           mean over valid rays x 3 of (rgb - rgbs)^2
+ *   depth           mean over valid & depths > 0 of (depth - depths)^2;  skipped if no depths > 0 at all
+ *   opacity         mean over valid of (clamp(opacity_instance, 0, 1) - instance_mask)^2 * instance_mask_weight
+ *   instance color  mean over valid & instance_mask (x 3) of (rgb_instance - rgbs)^2 * weight;  skipped if empty
+ *   instance depth  mean over valid & depths > 0 & instance_mask of (depth_instance - depths)^2 * weight;  skipped if empty
+ * loss_sum = sum of weight_t * term_t over the terms present.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct onerf_loss_maps {      /* maps of one pass, or their gradients (same shapes) */
+  const float* rgb;                   /* (N,3) */
+  const float* depth;                 /* (N,) */
+  const float* opacity_instance;      /* (N,) */
+  const float* rgb_instance;          /* (N,3) */
+  const float* depth_instance;        /* (N,) */
+} onerf_loss_maps;
+
+typedef struct onerf_loss_args {
+  int64_t n_rays;
+  int has_fine;
+  onerf_loss_maps coarse, fine;            /* inputs */
+  const float* rgbs;                       /* (N,3) batch["rgbs"] */
+  const float* depths;                     /* (N,)  batch["depths"] */
+  const uint8_t* valid_mask;               /* (N,)  batch["valid_mask"] */
+  const uint8_t* instance_mask;            /* (N,)  batch["instance_mask"] */
+  const float* instance_mask_weight;       /* (N,)  batch["instance_mask_weight"] */
+  float color_weight, depth_weight, opacity_weight, instance_color_weight, instance_depth_weight; /* config loss.*_weight */
+  onerf_loss_maps grad_coarse, grad_fine;  /* outputs (written): d(loss_sum)/d(map) */
+  float* loss_sum_out;                     /* (1,) */
+  float* terms_out;                        /* (5,) unweighted terms in the order above (0 where skipped) */
+  int32_t* present_out;                    /* (5,) 1 = term present, 0 = skipped (the reference returns None) */
+  void* workspace;                         /* onerf_total_loss_workspace_bytes() bytes, 8-byte aligned */
+} onerf_loss_args;
+
+size_t onerf_total_loss_workspace_bytes(void);
+int onerf_total_loss(onerf_ctx* ctx, const onerf_loss_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Backward building blocks (what loss.backward() does in the reference, train.py:180).
  * fp32.  object_nerf_b200/backward.py chains them into the gradient of render_rays.
  * ------------------------------------------------------------------------------------------- */

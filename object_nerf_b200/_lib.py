@@ -26,6 +26,7 @@ EXPORTS = [
     "onerf_sample_pdf_merge", "onerf_sample_pdf", "onerf_encode", "onerf_field_fwd", "onerf_composite", "onerf_composite_multi",
     "onerf_render_rays_workspace_bytes", "onerf_render_rays_fwd",
     "onerf_ray_directions", "onerf_get_rays", "onerf_generate_rays", "onerf_camera_rays",
+    "onerf_total_loss_workspace_bytes", "onerf_total_loss",
     "onerf_composite_bwd", "onerf_gemm", "onerf_leaky_bwd", "onerf_head_bwd", "onerf_segment_sum", "onerf_colsum",
     "onerf_dir_encode", "onerf_encode_bwd",
 ]
@@ -56,6 +57,20 @@ class CompositeArgs(C.Structure):
         ("frustum_bound_th", C.c_float), ("pass_through_mask", _p),
         ("weights", _p), ("opacity", _p), ("rgb", _p), ("depth", _p),
         ("rgb_instance", _p), ("depth_instance", _p), ("opacity_instance", _p),
+    ]
+
+
+class LossMaps(C.Structure):
+    _fields_ = [("rgb", _p), ("depth", _p), ("opacity_instance", _p), ("rgb_instance", _p), ("depth_instance", _p)]
+
+
+class LossArgs(C.Structure):
+    _fields_ = [
+        ("n_rays", C.c_int64), ("has_fine", C.c_int), ("coarse", LossMaps), ("fine", LossMaps), ("rgbs", _p), ("depths", _p),
+        ("valid_mask", _p), ("instance_mask", _p), ("instance_mask_weight", _p), ("color_weight", C.c_float),
+        ("depth_weight", C.c_float), ("opacity_weight", C.c_float), ("instance_color_weight", C.c_float),
+        ("instance_depth_weight", C.c_float), ("grad_coarse", LossMaps), ("grad_fine", LossMaps), ("loss_sum_out", _p),
+        ("terms_out", _p), ("present_out", _p), ("workspace", _p),
     ]
 
 
@@ -130,6 +145,8 @@ def load() -> C.CDLL:
         lib.onerf_generate_rays.argtypes = [_p, _p, _p, C.c_int64, C.POINTER(BoxHost), C.c_double, C.c_double, C.c_double, _p, _p, _p]
         lib.onerf_camera_rays.argtypes = [_p, C.c_int, C.c_int, C.c_float, C.POINTER(C.c_float), C.POINTER(BoxHost), C.c_double,
                                           C.c_double, C.c_double, _p, _p, _p]
+        lib.onerf_total_loss_workspace_bytes.restype = C.c_size_t
+        lib.onerf_total_loss.argtypes = [_p, C.POINTER(LossArgs), _p]
         lib.onerf_composite_multi.argtypes = [_p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_int, _p, _p, _p, _p, _p, _p, _p, _p]
         lib.onerf_composite_bwd.argtypes = [_p, C.POINTER(CompositeArgs), _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]
         lib.onerf_gemm.argtypes = [_p, _p, C.c_int, C.c_int, _p, C.c_int, _p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _p]

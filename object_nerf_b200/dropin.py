@@ -11,8 +11,9 @@ result keys as the reference files they shadow):
     models.embedding_helper       -> object_nerf_b200.embedding_helper  (Embedding, EmbeddingVoxel)
     models.code_library           -> object_nerf_b200.code_library      (CodeLibrary)
     render_tools.multi_rendering  -> object_nerf_b200.multi_rendering   (render_rays_multi)
+    models.losses                 -> object_nerf_b200.losses            (TotalLoss, get_loss: fused loss + gradient)
 
-Every other reference module (train.py, render_tools/editable_renderer.py, datasets/, utils/, models/losses.py)
+Every other reference module (train.py, render_tools/editable_renderer.py, datasets/, utils/)
 is imported from the reference checkout as is: their `from models.rendering import render_rays` etc. bind to
 the modules above because Python consults sys.modules before the file system.
 """
@@ -26,12 +27,13 @@ ALIASES = {
     "models.embedding_helper": "object_nerf_b200.embedding_helper",
     "models.code_library": "object_nerf_b200.code_library",
     "render_tools.multi_rendering": "object_nerf_b200.multi_rendering",
+    "models.losses": "object_nerf_b200.losses",
 }
 
 
 def install(reference_root=None):
     """Alias the hot-path modules.  reference_root (optional) is put on sys.path so that the remaining
-    reference packages (`models.losses`, `utils`, `datasets`, `render_tools.editable_renderer`) import."""
+    reference packages (`utils`, `datasets`, `render_tools.editable_renderer`) import."""
     if reference_root and reference_root not in sys.path:
         sys.path.insert(0, reference_root)
     for pkg in ("models", "render_tools"):

@@ -500,3 +500,61 @@ def generate_rays(obj_id, rays_o, rays_d, near, far, scale_factor, box=None, bbo
     bn[~mask] = 0
     bf[~mask] = 0
     return torch.cat([rays_o, rays_d, bn, bf], 1)
+
+
+# --------------------------------------------------------------------------------------------
+# training loss
+# --------------------------------------------------------------------------------------------
+LOSS_TERMS = ("color_loss", "depth_loss", "opacity_loss", "instance_color_loss", "instance_depth_loss")
+
+
+def total_loss(inputs, batch, conf):
+    """models/losses.py:5-135 (TotalLoss): five masked-MSE terms, each summed over the coarse and fine maps, times its
+    weight; a term whose mask is empty is skipped (returns None in the reference: :13-14, :46-47, :51-52, :80-81).
+    Returns (loss_sum, {term: unweighted value}) like the reference (:121-133)."""
+    mse = lambda a, b: (a - b) ** 2
+    vm = batch["valid_mask"].view(-1)
+    im = batch["instance_mask"].view(-1)
+    imw = batch["instance_mask_weight"].view(-1)
+    tgt_rgb, tgt_d = batch["rgbs"].view(-1, 3), batch["depths"].view(-1)
+    fine = "rgb_fine" in inputs
+    terms = {}
+    # ColorLoss (:67-98), scene
+    m3 = vm.view(-1, 1).repeat(1, 3)
+    loss = mse(inputs["rgb_coarse"][m3], tgt_rgb[m3]).mean()
+    if fine:
+        loss = loss + mse(inputs["rgb_fine"][m3], tgt_rgb[m3]).mean()
+    terms["color_loss"] = conf["color_loss_weight"] * loss
+    # DepthLoss (:36-64), scene
+    if (tgt_d > 0).sum() > 0:
+        dm = (vm * (tgt_d > 0)).view(-1)
+        loss = mse(inputs["depth_coarse"][dm], tgt_d[dm]).mean()
+        if fine:
+            loss = loss + mse(inputs["depth_fine"][dm], tgt_d[dm]).mean()
+        terms["depth_loss"] = conf["depth_loss_weight"] * loss
+    # OpacityLoss (:5-33)
+    if vm.sum() > 0:
+        w = imw[vm]
+        loss = (mse(torch.clamp(inputs["opacity_instance_coarse"][vm], 0, 1), im[vm].float()) * w).mean()
+        if "opacity_instance_fine" in inputs:
+            loss = loss + (mse(torch.clamp(inputs["opacity_instance_fine"][vm], 0, 1), im[vm].float()) * w).mean()
+        terms["opacity_loss"] = conf["opacity_loss_weight"] * loss
+    # ColorLoss, instance only (:79-91)
+    mi = m3 * im.view(-1, 1).repeat(1, 3)
+    if mi.sum() > 0:
+        w = imw.view(-1, 1).repeat(1, 3)[mi]
+        loss = (mse(inputs["rgb_instance_coarse"][mi], tgt_rgb[mi]) * w).mean()
+        if "rgb_instance_fine" in inputs:
+            loss = loss + (mse(inputs["rgb_instance_fine"][mi], tgt_rgb[mi]) * w).mean()
+        terms["instance_color_loss"] = conf["instance_color_loss_weight"] * loss
+    # DepthLoss, instance only (:48-59)
+    if (tgt_d > 0).sum() > 0:
+        dmi = (vm * (tgt_d > 0)).view(-1) * im
+        if dmi.sum() > 0:
+            w = imw[dmi]
+            loss = (mse(inputs["depth_instance_coarse"][dmi], tgt_d[dmi]) * w).mean()
+            if "depth_instance_fine" in inputs:
+                loss = loss + (mse(inputs["depth_instance_fine"][dmi], tgt_d[dmi]) * w).mean()
+            terms["instance_depth_loss"] = conf["instance_depth_loss_weight"] * loss
+    loss_sum = sum(terms.values())
+    return loss_sum, {k: v / conf[f"{k}_weight"] for k, v in terms.items()}

@@ -264,3 +264,34 @@ def build_bbox_case(c):
     d[zero, rng.integers(0, 3, size=int(zero.sum()))] = 0.0
     return dict(rays_o=torch.from_numpy(o), rays_d=torch.from_numpy(d), pose_avg=pose_avg, axis_align_mat=axis,
                 bbox_bounds=bounds, scale_factor=float(s), bbox_enlarge=float(c["enlarge"]), near=0.3, far=6.0)
+
+
+# ------------------------------------------------------------------------------------------------
+# training loss
+# ------------------------------------------------------------------------------------------------
+LOSS_CASES = {
+    "loss_train": dict(n=2048, fine=True, p_valid=0.9, p_inst=0.5, p_depth=0.8, seed=401),
+    "loss_coarse_only": dict(n=300, fine=False, p_valid=0.7, p_inst=0.3, p_depth=0.5, seed=402),
+    "loss_no_instance": dict(n=257, fine=True, p_valid=0.8, p_inst=0.0, p_depth=0.6, seed=403),   # instance terms skipped
+    "loss_no_depth": dict(n=64, fine=True, p_valid=1.0, p_inst=0.5, p_depth=0.0, seed=404),       # depth terms skipped
+}
+LOSS_MAP_KEYS = ("rgb", "depth", "opacity_instance", "rgb_instance", "depth_instance")
+
+
+def build_loss_case(c):
+    """Random rendered maps (opacity outside [0, 1] for some rays: the clamp) and a random batch
+    (datasets/generic_dataset.py keys consumed by models/losses.py)."""
+    rng = np.random.Generator(np.random.PCG64(c["seed"]))
+    n = c["n"]
+    f = lambda *shape: torch.from_numpy(rng.uniform(0, 1, size=shape).astype(np.float32))
+    maps = {}
+    for typ in (("coarse", "fine") if c["fine"] else ("coarse",)):
+        maps[f"rgb_{typ}"], maps[f"rgb_instance_{typ}"] = f(n, 3), f(n, 3)
+        maps[f"depth_{typ}"], maps[f"depth_instance_{typ}"] = f(n) * 3, f(n) * 3
+        maps[f"opacity_instance_{typ}"] = f(n) * 1.4 - 0.2
+    depths = f(n) * 3
+    depths[torch.from_numpy(rng.uniform(size=n) >= c["p_depth"])] = 0.0
+    im = torch.from_numpy(rng.uniform(size=n) < c["p_inst"])
+    batch = dict(rgbs=f(n, 3), depths=depths, valid_mask=torch.from_numpy(rng.uniform(size=n) < c["p_valid"]),
+                 instance_mask=im, instance_mask_weight=torch.where(im, torch.tensor(1.0), torch.tensor(0.05)))
+    return maps, batch

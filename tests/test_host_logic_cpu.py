@@ -25,6 +25,7 @@ def test_dropin_aliases_and_surface():
         from models.embedding_helper import Embedding, EmbeddingVoxel  # noqa: F401
         from models.code_library import CodeLibrary  # noqa: F401
         from render_tools.multi_rendering import render_rays_multi  # noqa: F401
+        from models.losses import get_loss, TotalLoss  # noqa: F401
         import object_nerf_b200.rendering as R
         assert render_rays is R.render_rays
     finally:

@@ -153,3 +153,22 @@ def test_ray_bbox_intersections_match_reference_golden(golden, name):
     # the cases exercise every rule of the slab test
     d = inp["rays_d"]
     assert (d == 0).any() and mask.any() and (~mask).any()
+
+
+# ------------------------------------------------------------------------------------------------
+# training loss
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", list(cases.LOSS_CASES))
+def test_total_loss_matches_reference_golden(golden, name):
+    maps, batch = cases.build_loss_case(cases.LOSS_CASES[name])
+    gold = golden(name)
+    maps = {k: v.clone().requires_grad_(True) for k, v in maps.items()}
+    loss_sum, terms = O.total_loss(maps, batch, cases.LOSS_CONF)
+    assert torch.equal(loss_sum.detach(), gold["loss_sum"])
+    assert {"term|" + k for k in terms} == {k for k in gold if k.startswith("term|")}
+    for k, v in terms.items():
+        assert torch.equal(v.detach(), gold["term|" + k]), k
+    loss_sum.backward()
+    for k, v in maps.items():
+        g = v.grad if v.grad is not None else torch.zeros_like(v)
+        assert torch.equal(g, gold["grad|" + k]), k

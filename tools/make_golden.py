@@ -262,9 +262,27 @@ def gen_ray_cases():
         print(name, "hits", int(mask.sum()), "of", mask.numel())
 
 
+def gen_loss_cases():
+    """the reference's TotalLoss (models/losses.py) and its autograd gradients on random maps."""
+    from models.losses import TotalLoss
+    for name, c in cases.LOSS_CASES.items():
+        maps, batch = cases.build_loss_case(c)
+        maps = {k: v.clone().requires_grad_(True) for k, v in maps.items()}
+        loss_sum, loss_dict = TotalLoss(dict(cases.LOSS_CONF))(maps, batch)
+        loss_sum.backward()
+        fix = {"loss_sum": loss_sum.detach()}
+        for k, v in loss_dict.items():
+            fix["term|" + k] = v.detach()
+        for k, v in maps.items():
+            fix["grad|" + k] = v.grad if v.grad is not None else torch.zeros_like(v)
+        save(name, **fix)
+        print(name, float(loss_sum.detach()), sorted(loss_dict))
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     gen_ray_cases()
+    gen_loss_cases()
     gen_gridbuild()
     gen_grad_case()
     gen_stage_cases()
