@@ -87,6 +87,31 @@ def inference_model(results: Dict[str, Any], model, embeddings: Dict[str, Any], 
     return
 
 
+
+def query_sigma(model, embedding_xyz, xyz: torch.Tensor, obj_code: Optional[torch.Tensor] = None,
+                chunk: int = 1 << 22, precision: Optional[str] = None) -> torch.Tensor:
+    """Density of the field at arbitrary points: the `sigma_only=True` consumers of the fused encode + MLP
+    (SURVEY.md section 8f row 4).  Replaces, in one call per chunk, the loop body of tools/extract_mesh.py:83-109
+    (`embedding_xyz(xyz)` then `nerf_fine.forward(..., sigma_only=True)["sigma"]`, or with `obj_id > 0`
+    `forward_instance(..., sigma_only=True)["inst_sigma"]` fed by one code-library row) and the density query of
+    EmbeddingVoxel.self_pruning_empty_voxels (models/embedding_helper.py:219-225).
+    xyz (B,3); obj_code None -> scene sigma (models/nerf_model.py:108-112), else (64,) -> object sigma (:140-144).
+    Returns raw sigma (B,) (no relu), fp32, on xyz's device."""
+    use_voxel = _is_voxel(embedding_xyz)
+    packed = engine.packed_for(model, use_voxel)
+    grid = _grid_of(embedding_xyz)
+    xyz = xyz.reshape(-1, 3).contiguous().float()
+    out = torch.empty(xyz.shape[0], dtype=torch.float32, device=xyz.device)
+    for i in range(0, xyz.shape[0], chunk):
+        pts = xyz[i:i + chunk]
+        n = pts.shape[0]
+        rays = torch.zeros(n, 8, dtype=torch.float32, device=xyz.device)   # directions are irrelevant for sigma
+        z = torch.zeros(n, 1, dtype=torch.float32, device=xyz.device)
+        scene, obj = engine.field(rays, z, packed, grid, code_row=obj_code, want_scene=obj_code is None,
+                                  want_object=obj_code is not None, precision=precision, xyz=pts.view(n, 1, 3))
+        out[i:i + n] = (scene if obj_code is None else obj)[:, 0, 3]
+    return out
+
 def _render_forward(cfg, rays, codes, keep=False):
     """The whole forward of render_rays on the CUDA kernels.  keep=True also returns what the backward needs."""
     rand = cfg["rand"]

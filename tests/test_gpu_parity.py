@@ -427,3 +427,28 @@ def test_training_step_gradients_match_reference_golden(golden):
         assert err <= 1e-2 * rms + 1e-8, (name, err, rms)
     nz = torch.nonzero(emb.embedding_space_ftr.weight.grad.abs().sum(1)).view(-1).cpu()
     assert torch.equal(nz, g["voxel|nonzero_rows"])
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_query_sigma_matches_oracle(precision):
+    """dense density queries (mesh extraction, voxel pruning) through the fused kernel."""
+    from object_nerf_b200 import query_sigma
+    c = cases.RENDER_CASES["eval_voxel"]
+    inp = cases.build_render_case(c)
+    model = helpers.make_model(inp["weights"]["fine"], True, DEV)
+    emb = helpers.GridModule(inp["grid"]).to(DEV)
+    g = torch.Generator().manual_seed(5)
+    lo = -inp["grid"]["offset"]
+    hi = lo + inp["grid"]["voxel_size"] * inp["grid"]["shape"].float()
+    xyz = lo + (hi - lo) * torch.rand(3000, 3, generator=g)            # inside the grid, some in empty voxels
+    xyz[:50] = xyz[:50] + 100.0                                          # far outside: zero voxel features
+    code = inp["codes"][0]
+    w, grid = inp["weights"]["fine"], grid_obj(inp["grid"])
+    dirs = torch.zeros(xyz.shape[0], 3)
+    want = O.field_eval(w, grid, xyz, dirs, code[None, :].expand(xyz.shape[0], -1))
+    got_s = query_sigma(model, emb, xyz.to(DEV), precision=precision).cpu()
+    got_o = query_sigma(model, emb, xyz.to(DEV), obj_code=code.to(DEV), chunk=1024, precision=precision).cpu()
+    tol = 2e-4 if precision == "fp32" else 3e-2
+    for got, k in ((got_s, "sigma"), (got_o, "inst_sigma")):
+        ref = want[k]
+        assert ((got - ref).abs() <= tol * (1 + ref.abs())).all(), (k, (got - ref).abs().max().item())
