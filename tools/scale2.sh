@@ -1,0 +1,2 @@
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 3 --warmup 3 2>/dev/null | tail -1 > gpurun_out/bench_n2.json; python -c "
+import json; d=json.load(open('gpurun_out/bench_n2.json')); print(d['n_gpus'], d['value'], d['e2e']['value'], d['ms_per_step'], d['config']['parallelism'])"
