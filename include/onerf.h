@@ -107,6 +107,10 @@ int onerf_sample_pdf(onerf_ctx* ctx, const float* bins, const float* weights, in
 int onerf_encode(onerf_ctx* ctx, const onerf_grid* grid, const float* xyz, int64_t n_points,
                  float* scene_in, float* obj_in, void* stream);
 
+/* Raw trilinear voxel features (no positional encoding), models/embedding_helper.py:354-411 with
+ * positional_embedding=False: xyz (B,3) -> out (B,24).  Used by the grid refinement (voxel_subdivision, :250-252). */
+int onerf_voxel_features(onerf_ctx* ctx, const onerf_grid* grid, const float* xyz, int64_t n_points, float* out, void* stream);
+
 /* Fused encode + two-branch MLP over all samples of a ray set,
  * models/rendering.py:85-137 (+ models/nerf_model.py:97-152, models/embedding_helper.py:325-411),
  * and render_tools/multi_rendering.py:16-93 for the one-branch-per-object editing variant. */

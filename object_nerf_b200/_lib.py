@@ -23,7 +23,7 @@ N_LINEAR = 20
 EXPORTS = [
     "onerf_abi_version", "onerf_last_error", "onerf_ctx_create", "onerf_ctx_destroy",
     "onerf_ctx_launch_count", "onerf_packed_weights_bytes", "onerf_pack_weights", "onerf_sample_coarse",
-    "onerf_sample_pdf_merge", "onerf_sample_pdf", "onerf_encode", "onerf_field_fwd", "onerf_composite", "onerf_composite_multi",
+    "onerf_sample_pdf_merge", "onerf_sample_pdf", "onerf_encode", "onerf_voxel_features", "onerf_field_fwd", "onerf_composite", "onerf_composite_multi",
     "onerf_render_rays_workspace_bytes", "onerf_render_rays_fwd",
     "onerf_ray_directions", "onerf_get_rays", "onerf_generate_rays", "onerf_camera_rays",
     "onerf_total_loss_workspace_bytes", "onerf_total_loss",
@@ -135,6 +135,7 @@ def load() -> C.CDLL:
         lib.onerf_sample_pdf_merge.argtypes = [_p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_int, _p, C.c_uint64, _p, _p]
         lib.onerf_sample_pdf.argtypes = [_p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_int, _p, C.c_uint64, _p, _p]
         lib.onerf_encode.argtypes = [_p, C.POINTER(Grid), _p, C.c_int64, _p, _p, _p]
+        lib.onerf_voxel_features.argtypes = [_p, C.POINTER(Grid), _p, C.c_int64, _p, _p]
         lib.onerf_field_fwd.argtypes = [_p, C.POINTER(FieldArgs), _p]
         lib.onerf_composite.argtypes = [_p, C.POINTER(CompositeArgs), _p]
         lib.onerf_render_rays_workspace_bytes.argtypes = [C.c_int, C.c_int, C.c_int]

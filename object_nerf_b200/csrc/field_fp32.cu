@@ -409,3 +409,33 @@ extern "C" int onerf_encode(onerf_ctx* ctx, const onerf_grid* grid, const float*
   ONERF_LAUNCH_CHECK(ctx);
   return ONERF_OK;
 }
+
+// Raw trilinear voxel features (no positional encoding): compute_voxel_features_sparse(xyz, trilinear_interpolate=True,
+// positional_embedding=False), models/embedding_helper.py:354-411 - what voxel_subdivision (:250-252) samples to
+// initialise the refined grid.  Same individually rounded arithmetic as the stand-alone encoder.
+namespace {
+__global__ void __launch_bounds__(256)
+voxel_features_kernel(onerf_grid grid, const float* __restrict__ xyz, int64_t n, float* __restrict__ out) {
+  const GridView g = load_grid_view(grid);
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    float f[24];
+    voxel_trilinear<0, 24, true>(g, xyz[e * 3 + 0], xyz[e * 3 + 1], xyz[e * 3 + 2], f);
+    float4* o = reinterpret_cast<float4*>(out + e * 24);
+#pragma unroll
+    for (int q = 0; q < 6; ++q) o[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+  }
+}
+}  // namespace
+
+extern "C" int onerf_voxel_features(onerf_ctx* ctx, const onerf_grid* grid, const float* xyz, int64_t n_points, float* out,
+                                    void* stream) {
+  ONERF_CHECK_ARG(ctx && grid && xyz && out, "null argument");
+  ONERF_CHECK_ARG(grid->table && grid->idx_map && grid->voxel_offset && grid->voxel_size && grid->voxel_shape, "null grid buffer");
+  ONERF_CHECK_ARG(n_points >= 0 && onerf_aligned16(out) && onerf_aligned16(grid->table), "bad count or misaligned buffer");
+  if (n_points == 0) return ONERF_OK;
+  int blocks = (int)((n_points + 255) / 256);
+  if (blocks > ctx->num_sms * 16) blocks = ctx->num_sms * 16;
+  voxel_features_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(*grid, xyz, n_points, out);
+  ONERF_LAUNCH_CHECK(ctx);
+  return ONERF_OK;
+}

@@ -84,3 +84,67 @@ class EmbeddingVoxel(nn.Module):
     def forward(self, xyz):
         scene, obj = engine.encode(xyz.reshape(-1, 3), self.grid_buffers())
         return scene, obj
+
+    # ---- cold path at epoch boundaries: grid maintenance (reference :202-302, called from train.py:140-145) ----
+    def _occupied(self):
+        idx_occu = torch.nonzero(self.voxel_occupancy)
+        voxel_xyz = idx_occu.float() * self.voxel_size - self.voxel_offset
+        return idx_occu, voxel_xyz
+
+    def self_pruning_empty_voxels(self, model, max_alpha_th=0.5, precision=None, _rand=None, _sigma_fn=None):
+        """Reference :202-245: drop every occupied voxel whose largest alpha over 16^3 jittered samples
+        (`1 - exp(-relu(sigma))`, scene branch of `model`) stays below max_alpha_th: occupancy -> False, index map -> -1.
+        The density comes from the fused kernel (`rendering.query_sigma`) instead of `self.forward` + `model(...,
+        sigma_only=True)` (upstream's call at :223 passes a tensor to `forward(inputs: dict)`; the intended semantics
+        are kept).  precision: arithmetic of the density query (None = the library default).  _rand: optional list of U[0,1) tensors, one (32 * 4096, 3) block per 32-voxel chunk (tests);
+        _sigma_fn(xyz) -> sigma overrides the density query (CPU tests of the grid logic)."""
+        from . import rendering
+        idx_occu, voxel_xyz = self._occupied()
+        n_occu = voxel_xyz.shape[0]
+        n_per_voxel, per_batch = 16 ** 3, 32
+        sigma_fn = _sigma_fn or (lambda pts: rendering.query_sigma(model, self, pts, precision=precision))
+        empty = []
+        for k, i in enumerate(range(0, n_occu, per_batch)):
+            centres = voxel_xyz[i:i + per_batch]
+            samples = centres[:, None, :].expand(-1, n_per_voxel, -1).reshape(-1, 3).clone()
+            r = _rand[k][:samples.shape[0]].to(samples) if _rand is not None else torch.rand_like(samples)
+            samples += r * self.voxel_size - self.voxel_size / 2
+            sigmas = sigma_fn(samples).reshape(-1)
+            alphas = 1 - torch.exp(-torch.relu(sigmas))
+            empty.append(alphas.view(-1, n_per_voxel).max(-1)[0] < max_alpha_th)
+        empty_mask = torch.cat(empty, 0) if empty else torch.zeros(0, dtype=torch.bool, device=voxel_xyz.device)
+        idx_empty = idx_occu[empty_mask, :]
+        self.voxel_occupancy[idx_empty[:, 0], idx_empty[:, 1], idx_empty[:, 2]] = False
+        self.voxel_idx_map[idx_empty[:, 0], idx_empty[:, 1], idx_empty[:, 2]] = -1
+        return int(idx_empty.shape[0])
+
+    def voxel_subdivision(self, _features_fn=None):
+        """Reference :247-302: halve the voxel size.  Every occupied voxel spawns its 8 children
+        (itertools.product([0, 1], repeat=3) order), whose features are the trilinear samples of the OLD grid at the
+        child positions (raw features, no positional encoding: `onerf_voxel_features`); occupancy / index map are
+        rebuilt at twice the resolution and the children's rows written into the feature table."""
+        idx_occu, voxel_xyz = self._occupied()
+        dev = voxel_xyz.device
+        target = self.voxel_size / 2
+        new_xyz = []
+        for cx in (0, 1):
+            for cy in (0, 1):
+                for cz in (0, 1):
+                    new_xyz.append(voxel_xyz + torch.tensor([cx, cy, cz], device=dev) * target)
+        new_xyz = torch.cat(new_xyz, 0)
+        new_coord = ((new_xyz + self.voxel_offset) / target).round().long()
+        features_fn = _features_fn or (lambda pts: engine.voxel_features(pts, self.grid_buffers()))
+        with torch.no_grad():
+            new_ftrs = features_fn(new_xyz)
+        self.voxel_size = target
+        self.voxel_shape *= 2
+        shape = [int(v) for v in self.voxel_shape]
+        occ = torch.zeros(shape, dtype=torch.bool, device=dev)
+        occ[new_coord[:, 0], new_coord[:, 1], new_coord[:, 2]] = True
+        self.voxel_occupancy = occ
+        self.voxel_count = self.voxel_shape[0] * self.voxel_shape[1] * self.voxel_shape[2]
+        self.generate_voxel_idx_map()
+        with torch.no_grad():
+            assign = self.voxel_idx_map[new_coord[:, 0], new_coord[:, 1], new_coord[:, 2]]
+            self.embedding_space_ftr.weight[assign] = new_ftrs.to(self.embedding_space_ftr.weight.dtype)
+        return int(torch.nonzero(self.voxel_occupancy).shape[0])

@@ -182,6 +182,15 @@ def encode(xyz, grid: Optional[GridBuffers]):
     return scene, obj
 
 
+def voxel_features(xyz, grid: GridBuffers):
+    """Raw trilinear features (B,24) of the sparse voxel grid at xyz (no positional encoding)."""
+    xyz = _f32(xyz).reshape(-1, 3)
+    out = torch.empty(xyz.shape[0], 24, dtype=torch.float32, device=xyz.device)
+    _lib.check(_lib.load().onerf_voxel_features(_lib.ctx(xyz.device), C.byref(grid.c), xyz.data_ptr(), xyz.shape[0],
+                                                out.data_ptr(), _lib.stream()))
+    return out
+
+
 def field(rays, z, packed, grid: Optional[GridBuffers], codes=None, code_row=None, want_scene=True,
           want_object=True, precision=None, xyz=None, mute_zero_rays=False, boxes=None, scene_out=None,
           obj_out=None, z_stride=None, out_stride=None, n_samples=None, activations=None):

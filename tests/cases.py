@@ -295,3 +295,26 @@ def build_loss_case(c):
     batch = dict(rgbs=f(n, 3), depths=depths, valid_mask=torch.from_numpy(rng.uniform(size=n) < c["p_valid"]),
                  instance_mask=im, instance_mask_weight=torch.where(im, torch.tensor(1.0), torch.tensor(0.05)))
     return maps, batch
+
+
+# ------------------------------------------------------------------------------------------------
+# voxel grid maintenance
+# ------------------------------------------------------------------------------------------------
+MAINT_CASE = dict(n_points=44, seed=501, max_voxels=4096, max_alpha_th=0.1236, sigma_gain=6.0, sigma_bias=0.0,
+                  extra=dict(pcd_path="maint", scene_center=[0.5, 0.5, 0.0], scale_factor=2.0, voxel_size=0.4, neighbor_marks=1))
+
+
+def build_maint_case():
+    """A tiny cloud (a few dozen occupied voxels: the reference prunes with 16^3 samples per voxel), a random feature
+    table and the fine model's weights."""
+    c = MAINT_CASE
+    rng = np.random.Generator(np.random.PCG64(c["seed"]))
+    pts = rng.uniform([0, 0, -0.6], [2.4, 2.0, 0.6], size=(c["n_points"], 3))
+    table = torch.from_numpy(rng.normal(0, 0.35, size=(c["max_voxels"], 24)).astype(np.float32))
+    weights = synth.make_weights(c["seed"] + 1, use_voxel=True, sigma_gain=c["sigma_gain"], sigma_bias=c["sigma_bias"])
+    return dict(points=pts, table=table, weights=weights)
+
+
+def maint_rand(n_chunks, seed=MAINT_CASE["seed"] + 7):
+    g = torch.Generator().manual_seed(seed)
+    return [torch.rand(32 * 16 ** 3, 3, generator=g) for _ in range(n_chunks)]

@@ -156,3 +156,58 @@ def test_ray_sharded_gather_world2_gloo(n):
     assert [parallel.shard_bounds(7, 2, r) for r in range(2)] == [(0, 4), (4, 7)]
     port = 29500 + os.getpid() % 1000 + n
     mp.spawn(_worker, args=(2, port, n), nprocs=2, join=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# voxel grid maintenance: the grid surgery of our EmbeddingVoxel against the reference's,
+# with the two device queries (raw trilinear features, density) supplied by the CPU oracle
+# ------------------------------------------------------------------------------------------------
+def _maint_embedding():
+    from object_nerf_b200.embedding_helper import EmbeddingVoxel
+    from tests import cases
+    inp, c = cases.build_maint_case(), cases.MAINT_CASE
+    emb = EmbeddingVoxel(24, 6, c["max_voxels"], c["extra"], points=inp["points"])
+    with torch.no_grad():
+        emb.embedding_space_ftr.weight.copy_(inp["table"])
+    return emb, inp
+
+
+def _oracle_grid(emb):
+    from oracle import onerf_oracle as O
+    return O.VoxelGrid(emb.voxel_offset, emb.voxel_size, emb.voxel_shape.tolist(), emb.voxel_idx_map,
+                       emb.embedding_space_ftr.weight.detach().clone())
+
+
+def _assert_grid_state(emb, gold, prefix):
+    n = int(torch.nonzero(emb.voxel_occupancy).shape[0])
+    assert torch.equal(emb.voxel_size, gold[prefix + "voxel_size"])
+    assert torch.equal(emb.voxel_shape, gold[prefix + "voxel_shape"])
+    assert torch.equal(emb.voxel_occupancy, gold[prefix + "voxel_occupancy"].bool())
+    assert torch.equal(emb.voxel_idx_map, gold[prefix + "voxel_idx_map"])
+    assert torch.equal(emb.embedding_space_ftr.weight.detach()[:n], gold[prefix + "table_rows"])
+
+
+def test_voxel_subdivision_matches_reference_golden(golden):
+    from oracle import onerf_oracle as O
+    emb, _ = _maint_embedding()
+    gold = golden("maint_subdivision")
+    _assert_grid_state(emb, gold, "before|")                       # the constructor agrees with the reference first
+    old = _oracle_grid(emb)
+    n_after = emb.voxel_subdivision(_features_fn=lambda pts: O.voxel_features(pts, old))
+    assert n_after == 8 * int(gold["before|table_rows"].shape[0])
+    _assert_grid_state(emb, gold, "subdiv|")
+
+
+def test_self_pruning_matches_reference_golden(golden):
+    from oracle import onerf_oracle as O
+    from tests import cases
+    emb, inp = _maint_embedding()
+    gold = golden("maint_pruning")
+    grid = _oracle_grid(emb)
+    n_occu = int(gold["n_before"])
+    sigma = lambda pts: O.field_eval(inp["weights"], grid, pts, torch.zeros_like(pts), None, want_object=False)["sigma"]
+    n_pruned = emb.self_pruning_empty_voxels(None, max_alpha_th=cases.MAINT_CASE["max_alpha_th"],
+                                             _rand=cases.maint_rand((n_occu + 31) // 32), _sigma_fn=sigma)
+    assert 0 < n_pruned < n_occu                                   # the case prunes some voxels and keeps others
+    assert torch.equal(emb.voxel_occupancy, gold["pruned|voxel_occupancy"].bool())
+    assert torch.equal(emb.voxel_idx_map, gold["pruned|voxel_idx_map"])

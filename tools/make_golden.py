@@ -279,9 +279,61 @@ def gen_loss_cases():
         print(name, float(loss_sum.detach()), sorted(loss_dict))
 
 
+def _maint_embedding():
+    inp = cases.build_maint_case()
+    c = cases.MAINT_CASE
+    R.register_pointcloud(c["extra"]["pcd_path"], inp["points"])
+    emb = EmbeddingVoxel(24, 6, c["max_voxels"], R.AttrDict(c["extra"]))
+    with torch.no_grad():
+        emb.embedding_space_ftr.weight.copy_(inp["table"])
+    return emb, inp
+
+
+def _grid_state(emb, prefix):
+    n = int(torch.nonzero(emb.voxel_occupancy).shape[0])
+    return {prefix + "voxel_size": emb.voxel_size.clone(), prefix + "voxel_shape": emb.voxel_shape.clone(),
+            prefix + "voxel_occupancy": emb.voxel_occupancy.clone(), prefix + "voxel_idx_map": emb.voxel_idx_map.clone(),
+            prefix + "table_rows": emb.embedding_space_ftr.weight.detach()[:n].clone()}
+
+
+def gen_maint_cases():
+    """EmbeddingVoxel.voxel_subdivision and self_pruning_empty_voxels of the reference
+    (models/embedding_helper.py:202-302).  The pruning routine calls `model(voxel_ftrs, sigma_only=True)` and unpacks two
+    results (:223) although ObjectNeRF.forward takes a dict and returns a dict; the adapter below gives it exactly that
+    call shape on top of the reference model (sigma of the scene branch), nothing else is touched."""
+    c = cases.MAINT_CASE
+    emb, inp = _maint_embedding()
+    fix = _grid_state(emb, "before|")
+    emb.voxel_subdivision()
+    fix.update(_grid_state(emb, "subdiv|"))
+    save("maint_subdivision", **fix)
+
+    emb, inp = _maint_embedding()
+    model = ref_model(inp["weights"], True)
+
+    def adapter(voxel_ftrs, sigma_only=True):
+        with torch.no_grad():
+            return model({"emb_xyz": voxel_ftrs}, sigma_only=True)["sigma"], None
+
+    n_occu = int(torch.nonzero(emb.voxel_occupancy).shape[0])
+    n_chunks = (n_occu + 31) // 32
+    rand = cases.maint_rand(n_chunks)
+    seq = []
+    for k in range(n_chunks):
+        n_here = min(32, n_occu - 32 * k) * 16 ** 3
+        seq.append(rand[k][:n_here])
+    with InjectRandom(seq, [], []):
+        emb.self_pruning_empty_voxels(adapter, max_alpha_th=c["max_alpha_th"])
+    fix = _grid_state(emb, "pruned|")
+    fix["n_before"] = torch.tensor(n_occu)
+    save("maint_pruning", **fix)
+    print("pruning:", n_occu, "->", int(torch.nonzero(emb.voxel_occupancy).shape[0]))
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     gen_ray_cases()
+    gen_maint_cases()
     gen_loss_cases()
     gen_gridbuild()
     gen_grad_case()
