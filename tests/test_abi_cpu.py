@@ -62,3 +62,45 @@ def test_product_does_not_import_oracle():
     for fn in os.listdir(pkg):
         if fn.endswith(".py"):
             assert "oracle" not in open(os.path.join(pkg, fn)).read(), fn
+
+
+def test_every_entry_point_rejects_a_null_context_with_a_message(lib):
+    """No GPU needed: argument validation runs before any CUDA call.  Every compute entry point must return a negative
+    status (never crash, never silently succeed) and leave a message in onerf_last_error()."""
+    from object_nerf_b200 import _lib
+    null = None
+    z = ctypes.c_void_p(0)
+    calls = {
+        "onerf_pack_weights": (null, 1, None, None, z, 0, z),
+        "onerf_sample_coarse": (null, z, 4, 8, 0, 0.0, z, 0, z, z),
+        "onerf_sample_pdf_merge": (null, z, z, 4, 8, 8, 1, z, 0, z, z),
+        "onerf_sample_pdf": (null, z, z, 4, 8, 8, 1, z, 0, z, z),
+        "onerf_encode": (null, None, z, 4, z, z, z),
+        "onerf_voxel_features": (null, None, z, 4, z, z),
+        "onerf_field_fwd": (null, None, z),
+        "onerf_composite": (null, None, z),
+        "onerf_composite_multi": (null, z, z, 4, 2, 8, 0, z, z, z, z, z, z, z, z),
+        "onerf_render_rays_fwd": (null, None, z),
+        "onerf_ray_directions": (null, 4, 4, 1.0, z, z),
+        "onerf_get_rays": (null, z, 4, None, z, z, z),
+        "onerf_generate_rays": (null, z, z, 4, None, 1.0, 0.1, 1.0, z, z, z),
+        "onerf_camera_rays": (null, 4, 4, 1.0, None, None, 1.0, 0.1, 1.0, z, z, z),
+        "onerf_total_loss": (null, None, z),
+        "onerf_composite_bwd": (null, None, z, z, z, z, z, z, z, z, z, z),
+        "onerf_gemm": (null, z, 4, 0, z, 4, z, 4, 4, 4, 4, 0, z),
+        "onerf_leaky_bwd": (null, z, 4, z, 4, 4, 4, z),
+        "onerf_head_bwd": (null, z, z, z, 4, z),
+        "onerf_segment_sum": (null, z, 4, z, 4, 4, 4, 4, z),
+        "onerf_colsum": (null, z, 4, 4, 4, z, z),
+        "onerf_dir_encode": (null, z, 4, z, z),
+        "onerf_encode_bwd": (null, None, z, z, 4, 4, z, z, 4, 0, 4, z, z),
+    }
+    helpers = {"onerf_abi_version", "onerf_last_error", "onerf_ctx_create", "onerf_ctx_destroy", "onerf_ctx_launch_count",
+               "onerf_packed_weights_bytes", "onerf_render_rays_workspace_bytes", "onerf_total_loss_workspace_bytes"}
+    assert set(calls) | helpers == set(_lib.EXPORTS)
+    for name, args in calls.items():
+        rc = getattr(lib, name)(*args)
+        assert rc < 0, name
+        assert len(lib.onerf_last_error()) > 0, name
+    assert lib.onerf_render_rays_workspace_bytes(1024, 64, 64) >= 1024 * (448 * 4 + 2 * 128 * 16)
+    assert lib.onerf_total_loss_workspace_bytes() >= 16 * 8
