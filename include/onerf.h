@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define ONERF_ABI_VERSION 1
+#define ONERF_ABI_VERSION 2
 
 typedef enum onerf_status {
   ONERF_OK = 0,
@@ -141,7 +141,13 @@ typedef struct onerf_field_args {
    * activations of the forward: [0] X (384 voxel / 64 plain), [1..8] scene hidden 1..8 (256), [9] scene final (256),
    * [10] scene dir (128), [11..14] object hidden 1..4 (128), [15] object final (128), [16] object dir (64). */
   float* const* activations;
+  /* training forward (ONERF_PREC_BF16, voxel model, dense z / outputs): if non-NULL, a workspace of
+   * onerf_field_train_bytes(n_rays * n_samples) bytes receiving what the tensor-core backward needs: every layer's
+   * output activations and the encoded input as bf16 tiles in the tensor cores' operand layout, and 1-bit LeakyReLU
+   * masks (object_nerf_b200/csrc/layout.h: TrainLayout). */
+  void* train_ws;
 } onerf_field_args;
+size_t onerf_field_train_bytes(int use_voxel, int64_t n_samples);
 #define ONERF_RAY_CONST_FLOATS 448
 
 int onerf_field_fwd(onerf_ctx* ctx, const onerf_field_args* args, void* stream);
@@ -208,6 +214,10 @@ typedef struct onerf_render_args {
   onerf_render_maps fine;       /* written iff n_importance > 0 */
   void* workspace;              /* >= onerf_render_rays_workspace_bytes(...) bytes, 256-byte aligned */
   size_t workspace_bytes;
+  /* training: if non-NULL (ONERF_PREC_BF16, voxel model), >= onerf_train_workspace_bytes(...) bytes, 1024-byte aligned;
+   * the forward then keeps both passes' per-sample fields and the backward operands there for onerf_render_rays_bwd. */
+  void* train_ws;
+  size_t train_ws_bytes;
 } onerf_render_args;
 
 size_t onerf_render_rays_workspace_bytes(int n_rays, int n_samples, int n_importance);
@@ -289,12 +299,70 @@ size_t onerf_total_loss_workspace_bytes(void);
 int onerf_total_loss(onerf_ctx* ctx, const onerf_loss_args* args, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
- * Backward building blocks (what loss.backward() does in the reference, train.py:180).
- * fp32.  object_nerf_b200/backward.py chains them into the gradient of render_rays.
+ * Training on the tensor cores (what loss.backward() does in the reference, train.py:147-180,
+ * through models/rendering.py, models/nerf_model.py:97-152, models/embedding_helper.py:354-409, models/code_library.py).
+ * onerf_render_rays_fwd with train_ws set runs the bf16 forward and keeps the backward operands;
+ * onerf_render_rays_bwd turns the upstream gradients of the rendered maps into gradients of the 2 x 20 nn.Linear
+ * tensors, the per-ray object codes and the voxel feature table:
+ *   compositing backward -> head gradients -> input-gradient chain (tcgen05, transposed weight images, operand resident
+ *   in TMEM) -> weight gradients (tcgen05, sample-axis reduction) -> encoding gradient (tcgen05 + scatter-add) ->
+ *   per-ray-constant columns (direction encoding, object code) -> reference [out,in] layout.
+ * No gradient flows to rays or depths (the importance samples are detached in the reference, models/rendering.py:307).
+ * ------------------------------------------------------------------------------------------- */
+size_t onerf_train_workspace_bytes(int use_voxel, int n_rays, int n_samples, int n_importance);
+
+typedef struct onerf_map_grads {   /* upstream gradients of one pass's maps; NULL = zero */
+  const float* rgb;              /* (N,3) */
+  const float* depth;            /* (N,) */
+  const float* opacity;          /* (N,) */
+  const float* rgb_instance;     /* (N,3) */
+  const float* depth_instance;   /* (N,) */
+  const float* opacity_instance; /* (N,) */
+} onerf_map_grads;
+
+typedef struct onerf_render_bwd_args {
+  onerf_map_grads coarse, fine;
+  const float* const* W_coarse;  /* the 20 reference weight tensors of models["coarse"] (onerf_pack_weights order) */
+  const float* const* W_fine;    /* ... of models["fine"]; required iff n_importance > 0 */
+  /* outputs, ACCUMULATED into (the caller zero-fills or keeps earlier contributions) */
+  float* const* dW_coarse;       /* 20 tensors shaped like W */
+  float* const* db_coarse;       /* 20 tensors shaped like b */
+  float* const* dW_fine;
+  float* const* db_fine;
+  float* d_codes;                /* (N,64); required iff forward_instance */
+  float* table_grad;             /* (n_rows,24) gradient of grid->table */
+} onerf_render_bwd_args;
+
+int onerf_render_rays_bwd(onerf_ctx* ctx, const onerf_render_args* fwd, const onerf_render_bwd_args* bwd, void* stream);
+
+/* stages of onerf_render_rays_bwd (tests / ncu).  ws = a field training workspace (onerf_field_train_bytes);
+ * dA_* (n_samples,4) = d(rgb_pre, sigma) per sample (onerf_head_bwd); grad = kernel-layout gradient buffer of
+ * onerf_grad_buffer_floats() floats, mapped to the reference layout by onerf_unpack_grads. */
+size_t onerf_grad_buffer_floats(int use_voxel);
+int onerf_unpack_grads(onerf_ctx* ctx, int use_voxel, const float* grad, float* const* dW, float* const* db, void* stream);
+int onerf_bwd_chain(onerf_ctx* ctx, int use_voxel, int want_object, const void* packed, void* ws, int64_t n_samples,
+                    const float* dA_scene, const float* dA_obj, void* stream);
+int onerf_bwd_wgrad(onerf_ctx* ctx, int use_voxel, int want_object, const void* ws, int64_t n_samples, float* grad, void* stream);
+int onerf_bwd_colsums(onerf_ctx* ctx, int use_voxel, int want_object, const void* ws, int64_t n_samples, const float* dA_scene,
+                      const float* dA_obj, float* grad, void* stream);
+int onerf_bwd_raysums(onerf_ctx* ctx, int use_voxel, int want_object, const void* ws, int n_rays, int n_samples, float* out,
+                      void* stream);
+int onerf_bwd_dx(onerf_ctx* ctx, int want_object, const void* packed, const void* ws, const float* rays, const float* z,
+                 int n_rays, int n_samples, const onerf_grid* grid, float* table_grad, void* stream);
+
+/* CodeLibrary.forward, models/code_library.py:18-28: out (n,64) = table[ids]; and its gradient (scatter-add by id). */
+int onerf_code_gather(onerf_ctx* ctx, const float* table, const int64_t* ids, int n, int n_codes, float* out, void* stream);
+int onerf_code_scatter_add(onerf_ctx* ctx, const float* d_codes, const int64_t* ids, int n, int n_codes, float* table_grad,
+                           void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * fp32 backward building blocks (verification arithmetic of the training path).
+ * object_nerf_b200/backward.py chains them into the gradient of render_rays for precision="fp32".
  * ------------------------------------------------------------------------------------------- */
 
-/* Gradient of onerf_composite w.r.t. the per-sample fields: fwd = the forward's arguments (noise buffers required when
- * noise_std > 0), depth_scene = forward scene depth (occlusion mask), g_* = upstream gradients of the maps (NULL = 0);
+/* Gradient of onerf_composite w.r.t. the per-sample fields: fwd = the forward's arguments (with noise_std > 0, NULL noise
+ * buffers replay the forward's Philox(seed) draw), depth_scene = forward scene depth (occlusion mask), g_* = upstream
+ * gradients of the maps (NULL = 0);
  * dscene / dobj (N,S,4) = d(r,g,b,sigma).  models/rendering.py:139-229 under autograd. */
 int onerf_composite_bwd(onerf_ctx* ctx, const onerf_composite_args* fwd, const float* depth_scene, const float* g_rgb,
                         const float* g_depth, const float* g_opacity, const float* g_rgb_inst, const float* g_depth_inst,

@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libonerf_sm100.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 PREC_FP32, PREC_BF16 = 0, 1
+ABI_VERSION = 2
 RAY_CONST_FLOATS = 448
 N_LINEAR = 20
 
@@ -29,6 +30,9 @@ EXPORTS = [
     "onerf_total_loss_workspace_bytes", "onerf_total_loss",
     "onerf_composite_bwd", "onerf_gemm", "onerf_leaky_bwd", "onerf_head_bwd", "onerf_segment_sum", "onerf_colsum",
     "onerf_dir_encode", "onerf_encode_bwd",
+    "onerf_field_train_bytes", "onerf_train_workspace_bytes", "onerf_render_rays_bwd", "onerf_grad_buffer_floats",
+    "onerf_unpack_grads", "onerf_bwd_chain", "onerf_bwd_wgrad", "onerf_bwd_colsums", "onerf_bwd_raysums", "onerf_bwd_dx",
+    "onerf_code_gather", "onerf_code_scatter_add",
 ]
 
 _p = C.c_void_p
@@ -45,7 +49,7 @@ class FieldArgs(C.Structure):
         ("want_scene", C.c_int), ("want_object", C.c_int), ("precision", C.c_int),
         ("mute_zero_rays", C.c_int), ("boxes", _p), ("n_boxes", C.c_int),
         ("scene_out", _p), ("obj_out", _p), ("out_stride", C.c_int64), ("ray_const", _p),
-        ("activations", C.POINTER(_p)),
+        ("activations", C.POINTER(_p)), ("train_ws", _p),
     ]
 
 
@@ -92,8 +96,19 @@ class RenderArgs(C.Structure):
         ("noise_obj_fine", _p), ("white_back", C.c_int), ("forward_instance", C.c_int), ("is_eval", C.c_int),
         ("zero_last_delta", C.c_int), ("rays_in_bbox", C.c_int), ("frustum_bound_th", C.c_float),
         ("pass_through_mask", _p), ("coarse", RenderMaps), ("fine", RenderMaps), ("workspace", _p),
-        ("workspace_bytes", C.c_size_t),
+        ("workspace_bytes", C.c_size_t), ("train_ws", _p), ("train_ws_bytes", C.c_size_t),
     ]
+
+
+class MapGrads(C.Structure):
+    _fields_ = [("rgb", _p), ("depth", _p), ("opacity", _p), ("rgb_instance", _p), ("depth_instance", _p),
+                ("opacity_instance", _p)]
+
+
+class RenderBwdArgs(C.Structure):
+    _fields_ = [("coarse", MapGrads), ("fine", MapGrads), ("W_coarse", C.POINTER(_p)), ("W_fine", C.POINTER(_p)),
+                ("dW_coarse", C.POINTER(_p)), ("db_coarse", C.POINTER(_p)), ("dW_fine", C.POINTER(_p)),
+                ("db_fine", C.POINTER(_p)), ("d_codes", _p), ("table_grad", _p)]
 
 
 def build(verbose: bool = False) -> str:
@@ -157,7 +172,22 @@ def load() -> C.CDLL:
         lib.onerf_colsum.argtypes = [_p, _p, C.c_int, C.c_int64, C.c_int, _p, _p]
         lib.onerf_dir_encode.argtypes = [_p, _p, C.c_int, _p, _p]
         lib.onerf_encode_bwd.argtypes = [_p, C.POINTER(Grid), _p, _p, C.c_int, C.c_int, _p, _p, C.c_int, C.c_int64, C.c_int64, _p, _p]
-        if lib.onerf_abi_version() != 1:
+        lib.onerf_field_train_bytes.argtypes = [C.c_int, C.c_int64]
+        lib.onerf_field_train_bytes.restype = C.c_size_t
+        lib.onerf_train_workspace_bytes.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
+        lib.onerf_train_workspace_bytes.restype = C.c_size_t
+        lib.onerf_render_rays_bwd.argtypes = [_p, C.POINTER(RenderArgs), C.POINTER(RenderBwdArgs), _p]
+        lib.onerf_grad_buffer_floats.argtypes = [C.c_int]
+        lib.onerf_grad_buffer_floats.restype = C.c_size_t
+        lib.onerf_unpack_grads.argtypes = [_p, C.c_int, _p, C.POINTER(_p), C.POINTER(_p), _p]
+        lib.onerf_bwd_chain.argtypes = [_p, C.c_int, C.c_int, _p, _p, C.c_int64, _p, _p, _p]
+        lib.onerf_bwd_wgrad.argtypes = [_p, C.c_int, C.c_int, _p, C.c_int64, _p, _p]
+        lib.onerf_bwd_colsums.argtypes = [_p, C.c_int, C.c_int, _p, C.c_int64, _p, _p, _p, _p]
+        lib.onerf_bwd_raysums.argtypes = [_p, C.c_int, C.c_int, _p, C.c_int, C.c_int, _p, _p]
+        lib.onerf_bwd_dx.argtypes = [_p, C.c_int, _p, _p, _p, _p, C.c_int, C.c_int, C.POINTER(Grid), _p, _p]
+        lib.onerf_code_gather.argtypes = [_p, _p, _p, C.c_int, C.c_int, _p, _p]
+        lib.onerf_code_scatter_add.argtypes = [_p, _p, _p, C.c_int, C.c_int, _p, _p]
+        if lib.onerf_abi_version() != ABI_VERSION:
             raise RuntimeError("libonerf_sm100.so ABI version mismatch")
         _lib = lib
         return lib

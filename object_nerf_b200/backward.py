@@ -2,6 +2,12 @@
 (reference: loss.backward() through models/rendering.py, models/nerf_model.py, models/embedding_helper.py and
 models/code_library.py).
 
+Two arithmetics, selected by `precision`:
+  bf16 (default)  RenderRaysTcFn: ONE C call forward (onerf_render_rays_fwd with a training workspace: the tcgen05 forward
+                  keeps every layer's activations as bf16 operand tiles) and ONE C call backward (onerf_render_rays_bwd:
+                  tcgen05 input-gradient chain, weight-gradient and encoding-gradient GEMMs).  Voxel model only.
+  fp32            RenderRaysFn below: the verification path (FFMA forward re-run with fp32 activation dump, fp32 GEMMs).
+
 Gradients are produced for exactly what the reference trains: the 2 x 40 nn.Linear tensors of the coarse and fine
 ObjectNeRF, the per-ray object codes (-> CodeLibrary's embedding table through autograd of the lookup) and the
 voxel feature table.  No gradient flows to rays or depths (the importance samples are detached in the reference,
@@ -92,7 +98,7 @@ def field_backward(model, emb_xyz, rays, z, codes, dscene, dobj, want_object=Tru
     ops = _Ops(dev)
     use_voxel = hasattr(emb_xyz, "voxel_idx_map")
     grid = engine.GridBuffers.from_module(emb_xyz) if use_voxel else None
-    packed = engine.packed_for(model, use_voxel)
+    packed = engine.packed_for(model, use_voxel, fresh=True)
     lin = engine.model_linears(model)
     W = [engine._f32(w.detach()) for w, _ in lin]
     dWb = [(torch.zeros_like(w, dtype=torch.float32), torch.zeros_like(b, dtype=torch.float32)) for w, b in lin]
@@ -261,3 +267,159 @@ class RenderRaysFn(torch.autograd.Function):
                 flat += [gw[i][0], gw[i][1]] if gw is not None else [None, None]
         assert len(flat) == ctx.n_params
         return (None, None, d_codes_total) + tuple(flat)
+
+
+# ------------------------------------------------------------------------------------------------
+# tensor-core training path
+# ------------------------------------------------------------------------------------------------
+class _WsPool:
+    """Training workspaces are large (2.6 MB per ray at 64 + 128 samples): keep them across steps.  A workspace is leased
+    to one autograd graph (forward -> backward) and returns to the pool when that graph is released."""
+
+    def __init__(self):
+        self.free = {}
+
+    def take(self, nbytes, dev):
+        lst = self.free.setdefault((nbytes, dev), [])
+        if lst:
+            return lst.pop()
+        t = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
+        off = (-t.data_ptr()) % 1024
+        return t[off:off + nbytes]
+
+    def give(self, t):
+        lst = self.free.setdefault((t.numel(), t.device), [])
+        if len(lst) < 2:
+            lst.append(t)
+
+
+_pool = _WsPool()
+
+
+class _Lease:
+    def __init__(self, t):
+        self.t = t
+
+    def __del__(self):
+        try:
+            _pool.give(self.t)
+        except Exception:
+            pass
+
+
+class RenderRaysTcFn(torch.autograd.Function):
+    """Differentiable render_rays on the tensor cores.  Inputs after `cfg`: rays, codes, then the flat list of trainable
+    tensors ([voxel table] + coarse 40 + fine 40), as assembled by rendering.render_rays."""
+
+    @staticmethod
+    def forward(ctx, cfg, rays, codes, *params):
+        lib = _lib.load()
+        dev = rays.device
+        emb = cfg["embeddings"]["xyz"]
+        n = rays.shape[0]
+        ns, ni = cfg["N_samples"], cfg["N_importance"]
+        fi = cfg["forward_instance"]
+        rand = cfg["rand"]
+        f = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=dev)
+        grid = engine.GridBuffers.from_module(emb)
+        keep = [rays, grid]
+        a = _lib.RenderArgs()
+        packed, lins = {}, {}
+        for typ in cfg["model_order"]:
+            lins[typ] = engine.model_linears(cfg["models"][typ])
+            packed[typ] = engine.packed_for(cfg["models"][typ], True, fresh=True)
+        maps = {}
+        for typ, s in (("coarse", ns), ("fine", ns + ni)):
+            if typ == "fine" and ni == 0:
+                continue
+            m = dict(weights=f(n, s), opacity=f(n), z_vals=f(n, s), rgb=f(n, 3), depth=f(n))
+            if fi:
+                m.update(rgb_instance=f(n, 3), depth_instance=f(n), opacity_instance=f(n))
+            maps[typ] = m
+            cm = getattr(a, typ)
+            for k, v in m.items():
+                setattr(cm, k, v.data_ptr())
+        ws_bytes = lib.onerf_render_rays_workspace_bytes(n, ns, ni)
+        workspace = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=dev)
+        tws_bytes = lib.onerf_train_workspace_bytes(1, n, ns, ni)
+        lease = _Lease(_pool.take(tws_bytes, dev))
+        codes_c = engine._f32(codes.detach()) if (codes is not None and fi) else None
+        mask = cfg["pass_through_mask"]
+        mask = mask.reshape(-1).to(torch.uint8).contiguous() if mask is not None else None
+        opt = {k: (engine._f32(rand[k]) if rand.get(k) is not None else None)
+               for k in ("jitter", "u", "noise_scene_coarse", "noise_obj_coarse", "noise_scene_fine", "noise_obj_fine")}
+        keep += [codes_c, mask, opt, workspace, packed]
+        a.rays, a.codes = rays.data_ptr(), _lib.ptr(codes_c)
+        a.n_rays, a.n_samples, a.n_importance = n, ns, ni
+        a.grid = C.pointer(grid.c)
+        a.packed_coarse = packed["coarse"].data_ptr()
+        a.packed_fine = packed["fine"].data_ptr() if ni > 0 else None
+        a.precision = _lib.PREC_BF16
+        seed = engine.new_seed() if (cfg["perturb"] > 0 or cfg["noise_std"] > 0) else 0
+        a.use_disp, a.perturb, a.noise_std, a.seed = int(cfg["use_disp"]), cfg["perturb"], cfg["noise_std"], seed
+        a.jitter, a.u = _lib.ptr(opt["jitter"]), _lib.ptr(opt["u"])
+        a.noise_scene_coarse, a.noise_obj_coarse = _lib.ptr(opt["noise_scene_coarse"]), _lib.ptr(opt["noise_obj_coarse"])
+        a.noise_scene_fine, a.noise_obj_fine = _lib.ptr(opt["noise_scene_fine"]), _lib.ptr(opt["noise_obj_fine"])
+        a.white_back, a.forward_instance, a.is_eval = int(cfg["white_back"]), int(fi), int(cfg["is_eval"])
+        a.zero_last_delta, a.rays_in_bbox = int(cfg["zero_last_delta"]), int(cfg["rays_in_bbox"])
+        a.frustum_bound_th = cfg["frustum_bound_th"]
+        a.pass_through_mask = _lib.ptr(mask)
+        a.workspace, a.workspace_bytes = workspace.data_ptr(), workspace.numel()
+        a.train_ws, a.train_ws_bytes = lease.t.data_ptr(), lease.t.numel()
+        with torch.cuda.device(dev):
+            _lib.check(lib.onerf_render_rays_fwd(_lib.ctx(dev), C.byref(a), _lib.stream()))
+        out = {f"{k}_{typ}": v for typ, m in maps.items() for k, v in m.items()}
+        ctx.args, ctx.keep, ctx.lease, ctx.lins, ctx.cfg = a, keep, lease, lins, cfg
+        ctx.n_params = len(params)
+        ctx.has_codes = codes_c is not None
+        keys = sorted(out)
+        ctx.keys = keys
+        tensors = tuple(out[k] for k in keys)
+        ctx.mark_non_differentiable(*[t for k, t in zip(keys, tensors) if k.startswith(("weights_", "z_vals_"))])
+        return tensors
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        lib = _lib.load()
+        a, cfg = ctx.args, ctx.cfg
+        dev = ctx.keep[0].device
+        g = {k: (v.contiguous().float() if v is not None else None) for k, v in zip(ctx.keys, gouts)}
+        b = _lib.RenderBwdArgs()
+        keep = [g]
+        for typ in cfg["model_order"]:
+            mg = getattr(b, typ)
+            for name in ("rgb", "depth", "opacity", "rgb_instance", "depth_instance", "opacity_instance"):
+                setattr(mg, name, _lib.ptr(g.get(f"{name}_{typ}")))
+        grads = {}
+        for typ in cfg["model_order"]:
+            lin = ctx.lins[typ]
+            ws = [engine._f32(w.detach()) for w, _ in lin]
+            sizes = [t.numel() for pair in lin for t in pair]
+            flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)   # one fill for the 40 gradient tensors
+            views, o = [], 0
+            for (w, bb) in lin:
+                views.append((flat[o:o + w.numel()].view_as(w), flat[o + w.numel():o + w.numel() + bb.numel()].view_as(bb)))
+                o += w.numel() + bb.numel()
+            grads[typ] = views
+            Wp = (C.c_void_p * 20)(*[t.data_ptr() for t in ws])
+            dWp = (C.c_void_p * 20)(*[v[0].data_ptr() for v in views])
+            dbp = (C.c_void_p * 20)(*[v[1].data_ptr() for v in views])
+            keep += [ws, Wp, dWp, dbp]
+            setattr(b, "W_" + typ, Wp)
+            setattr(b, "dW_" + typ, dWp)
+            setattr(b, "db_" + typ, dbp)
+        d_codes = torch.zeros(a.n_rays, 64, dtype=torch.float32, device=dev) if ctx.has_codes else None
+        table = cfg["embeddings"]["xyz"].embedding_space_ftr.weight
+        table_grad = torch.zeros_like(table, dtype=torch.float32) if cfg["has_table"] else None
+        b.d_codes, b.table_grad = _lib.ptr(d_codes), _lib.ptr(table_grad)
+        with torch.cuda.device(dev):
+            _lib.check(lib.onerf_render_rays_bwd(_lib.ctx(dev), C.byref(a), C.byref(b), _lib.stream()))
+        flat_out: List[Optional[torch.Tensor]] = []
+        if cfg["has_table"]:
+            flat_out.append(table_grad)
+        for typ in cfg["model_order"]:
+            for w, bb in grads[typ]:
+                flat_out += [w, bb]
+        assert len(flat_out) == ctx.n_params
+        ctx.lease = None     # the workspace goes back to the pool
+        return (None, None, d_codes) + tuple(flat_out)

@@ -3,6 +3,7 @@
 #include <string.h>
 
 #include "field_common.cuh"
+#include "train_ws.h"
 
 static thread_local char g_err[512] = "";
 
@@ -33,11 +34,13 @@ extern "C" int onerf_ctx_create(int device, onerf_ctx** out) {
   c->device = device;
   c->num_sms = prop.multiProcessorCount;
   c->launches = 0;
+  c->pack_tables = nullptr;
   *out = c;
   return ONERF_OK;
 }
 
 extern "C" int onerf_ctx_destroy(onerf_ctx* ctx) {
+  if (ctx) onerf_free_pack_tables(ctx);
   delete ctx;
   return ONERF_OK;
 }
@@ -83,6 +86,14 @@ extern "C" int onerf_field_fwd(onerf_ctx* ctx, const onerf_field_args* a, void* 
     for (int i = 0; i < 10; ++i) p.dump_s[i] = a->activations[1 + i];
     for (int i = 0; i < 6; ++i) p.dump_o[i] = a->activations[11 + i];
   }
+  if (a->train_ws) {
+    ONERF_UNSUPPORTED(a->precision != ONERF_PREC_BF16, "the training dump is written by the tensor-core (bf16) kernel");
+    ONERF_UNSUPPORTED(!a->want_scene, "the training dump needs the scene branch");
+    ONERF_UNSUPPORTED(a->z_stride != a->n_samples || a->out_stride != a->n_samples || a->xyz, "training dump needs dense z / outputs and no explicit xyz");
+    ONERF_UNSUPPORTED(a->mute_zero_rays || a->n_boxes > 0, "editing extras have no backward");
+    ONERF_CHECK_ARG((reinterpret_cast<uintptr_t>(a->train_ws) & 1023u) == 0, "train_ws must be 1024-byte aligned");
+    p.train_ws = a->train_ws;
+  }
   int rc = onerf_launch_ray_const(ctx, p, stream);
   if (rc != ONERF_OK) return rc;
   if (a->precision == ONERF_PREC_FP32) return onerf_launch_field_fp32(ctx, p, stream);
@@ -106,9 +117,10 @@ extern "C" size_t onerf_render_rays_workspace_bytes(int n_rays, int n_samples, i
 
 static int render_pass(onerf_ctx* ctx, const onerf_render_args* a, const void* packed, const float* z, int S,
                        const onerf_render_maps& m, const float* noise_scene, const float* noise_obj, uint64_t seed,
-                       float* ray_const, float* scene, float* obj, void* stream) {
+                       float* ray_const, float* scene, float* obj, void* train_ws, void* stream) {
   onerf_field_args f;
   memset(&f, 0, sizeof(f));
+  f.train_ws = train_ws;
   f.rays = a->rays; f.z = z; f.z_stride = S;
   f.codes = a->forward_instance ? a->codes : nullptr;
   f.n_rays = a->n_rays; f.n_samples = S;
@@ -159,15 +171,31 @@ extern "C" int onerf_render_rays_fwd(onerf_ctx* ctx, const onerf_render_args* a,
   float* scene = reinterpret_cast<float*>(ws);
   ws += align256((size_t)a->n_rays * SF * 4 * sizeof(float));
   float* obj = reinterpret_cast<float*>(ws);
+  // training: both passes' fields and the backward operands are kept in the training workspace
+  float *scene_c = scene, *obj_c = obj, *scene_f = scene, *obj_f = obj;
+  void *tl_c = nullptr, *tl_f = nullptr;
+  if (a->train_ws) {
+    ONERF_UNSUPPORTED(!a->grid || a->precision != ONERF_PREC_BF16, "training workspace: bf16 voxel model only");
+    ONERF_CHECK_ARG((reinterpret_cast<uintptr_t>(a->train_ws) & 1023u) == 0, "train_ws must be 1024-byte aligned");
+    const TrainWs W = onerf_make_train_ws(1, a->n_rays, a->n_samples, a->n_importance);
+    if (a->train_ws_bytes < (size_t)W.total) {
+      onerf_set_error("onerf_render_rays_fwd: training workspace too small (%zu < %lld)", a->train_ws_bytes, (long long)W.total);
+      return ONERF_ERR_WORKSPACE;
+    }
+    char* t = reinterpret_cast<char*>(a->train_ws);
+    scene_c = reinterpret_cast<float*>(t + W.scene_c); obj_c = reinterpret_cast<float*>(t + W.obj_c);
+    scene_f = reinterpret_cast<float*>(t + W.scene_f); obj_f = reinterpret_cast<float*>(t + W.obj_f);
+    tl_c = t + W.tl_coarse; tl_f = t + W.tl_fine;
+  }
   // seeds: coarse depths, coarse noise, importance u, fine noise (rendering.py::_render_forward)
   int rc = onerf_sample_coarse(ctx, a->rays, a->n_rays, S, a->use_disp, a->perturb, a->jitter, a->seed, a->coarse.z_vals, stream);
   if (rc != ONERF_OK) return rc;
   rc = render_pass(ctx, a, a->packed_coarse, a->coarse.z_vals, S, a->coarse, a->noise_scene_coarse, a->noise_obj_coarse,
-                   a->seed + 1, ray_const, scene, obj, stream);
+                   a->seed + 1, ray_const, scene_c, obj_c, tl_c, stream);
   if (rc != ONERF_OK || a->n_importance == 0) return rc;
   rc = onerf_sample_pdf_merge(ctx, a->coarse.z_vals, a->coarse.weights, a->n_rays, S, a->n_importance, a->perturb == 0.0f ? 1 : 0,
                               a->u, a->seed + 2, a->fine.z_vals, stream);
   if (rc != ONERF_OK) return rc;
   return render_pass(ctx, a, a->packed_fine, a->fine.z_vals, SF, a->fine, a->noise_scene_fine, a->noise_obj_fine, a->seed + 3,
-                     ray_const, scene, obj, stream);
+                     ray_const, scene_f, obj_f, tl_f, stream);
 }

@@ -42,7 +42,7 @@ struct BranchGrad {
 // smem (per warp): alpha[S], trans[S], gw[S]
 __device__ __forceinline__ void composite_branch_bwd(const float* __restrict__ z, const float4* __restrict__ field, int S,
                                                      float last_delta, float noise_std, const float* __restrict__ noise,
-                                                     bool use_mask, float z_limit, bool white, float g_r, float g_g,
+                                                     uint64_t seed, uint32_t stream_id, int ray, bool use_mask, float z_limit, bool white, float g_r, float g_g,
                                                      float g_b, float g_d, float g_o, float4* __restrict__ dfield,
                                                      float* s_alpha, float* s_trans, float* s_gw, int lane) {
   // forward recompute
@@ -54,7 +54,10 @@ __device__ __forceinline__ void composite_branch_bwd(const float* __restrict__ z
       const float zi = __ldg(z + i);
       const float delta = (i + 1 < S) ? __fsub_rn(__ldg(z + i + 1), zi) : last_delta;
       float s = __ldg(field + i).w;
-      if (noise_std > 0.0f && noise) s = __fadd_rn(s, __fmul_rn(__ldg(noise + i), noise_std));
+      if (noise_std > 0.0f) {   // the forward's noise: the caller's buffer, or the same Philox draw (composite.cu)
+        const float nz = noise ? __ldg(noise + i) : philox_normal(seed, stream_id, (uint64_t)ray * S + i);
+        s = __fadd_rn(s, __fmul_rn(nz, noise_std));
+      }
       alpha = __fsub_rn(1.0f, expf(__fmul_rn(-delta, fmaxf(s, 0.0f))));
       if (use_mask && z_limit < zi) alpha = 0.0f;
     }
@@ -95,7 +98,10 @@ __device__ __forceinline__ void composite_branch_bwd(const float* __restrict__ z
       const float delta = (i + 1 < S) ? __fsub_rn(__ldg(z + i + 1), zi) : last_delta;
       const float4 f = __ldg(field + i);
       float s = f.w;
-      if (noise_std > 0.0f && noise) s = __fadd_rn(s, __fmul_rn(__ldg(noise + i), noise_std));
+      if (noise_std > 0.0f) {
+        const float nz = noise ? __ldg(noise + i) : philox_normal(seed, stream_id, (uint64_t)ray * S + i);
+        s = __fadd_rn(s, __fmul_rn(nz, noise_std));
+      }
       const float t = __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f);
       const float dalpha = gw * T - after / t;
       const bool masked = use_mask && z_limit < zi;
@@ -128,7 +134,7 @@ __global__ void __launch_bounds__(128) composite_bwd_kernel(CompositeBwdArgs a) 
     auto g1 = [&](const float* p) { return p ? __ldg(p + r) : 0.0f; };
     composite_branch_bwd(z, reinterpret_cast<const float4*>(a.fwd.scene) + (int64_t)r * S, S,
                          a.fwd.zero_last_delta ? 0.0f : 1e10f, a.fwd.noise_std,
-                         a.fwd.noise_scene ? a.fwd.noise_scene + (int64_t)r * S : nullptr, false, 0.0f,
+                         a.fwd.noise_scene ? a.fwd.noise_scene + (int64_t)r * S : nullptr, a.fwd.seed, 2u, r, false, 0.0f,
                          a.fwd.white_back != 0, g3(a.gs.g_rgb, 0), g3(a.gs.g_rgb, 1), g3(a.gs.g_rgb, 2), g1(a.gs.g_depth),
                          g1(a.gs.g_opacity), reinterpret_cast<float4*>(a.dscene) + (int64_t)r * S, s_alpha, s_trans, s_gw,
                          lane);
@@ -138,7 +144,7 @@ __global__ void __launch_bounds__(128) composite_bwd_kernel(CompositeBwdArgs a) 
       if (use_mask && a.fwd.pass_through_mask && a.fwd.pass_through_mask[r]) use_mask = false;
       const float z_limit = __fadd_rn(__ldg(a.depth_scene + r), a.fwd.frustum_bound_th);
       composite_branch_bwd(z, reinterpret_cast<const float4*>(a.fwd.obj) + (int64_t)r * S, S, 0.0f, a.fwd.noise_std,
-                           a.fwd.noise_obj ? a.fwd.noise_obj + (int64_t)r * S : nullptr, use_mask, z_limit, true,
+                           a.fwd.noise_obj ? a.fwd.noise_obj + (int64_t)r * S : nullptr, a.fwd.seed, 3u, r, use_mask, z_limit, true,
                            g3(a.go.g_rgb, 0), g3(a.go.g_rgb, 1), g3(a.go.g_rgb, 2), g1(a.go.g_depth), g1(a.go.g_opacity),
                            reinterpret_cast<float4*>(a.dobj) + (int64_t)r * S, s_alpha, s_trans, s_gw, lane);
       __syncwarp();
@@ -334,8 +340,6 @@ extern "C" int onerf_composite_bwd(onerf_ctx* ctx, const onerf_composite_args* f
                                    float* dscene, float* dobj, void* stream) {
   ONERF_CHECK_ARG(ctx && fwd && fwd->z && fwd->scene && dscene, "null argument");
   ONERF_CHECK_ARG(!fwd->obj || (dobj && depth_scene), "object branch needs dobj and depth_scene");
-  ONERF_UNSUPPORTED(fwd->noise_std > 0.0f && (!fwd->noise_scene || (fwd->obj && !fwd->noise_obj)),
-                    "backward needs the forward's noise buffers (device RNG noise is not replayed)");
   ONERF_UNSUPPORTED(fwd->n_samples > 2048, "S > 2048");
   if (fwd->n_rays == 0) return ONERF_OK;
   CompositeBwdArgs a;

@@ -10,7 +10,9 @@ struct onerf_ctx {
   int device;
   int num_sms;
   int64_t launches;
+  void* pack_tables;   // pack.cu: per-layout job tables in device memory (created on first use)
 };
+void onerf_free_pack_tables(onerf_ctx* ctx);
 
 void onerf_set_error(const char* fmt, ...);
 

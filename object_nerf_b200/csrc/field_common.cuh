@@ -28,6 +28,9 @@ struct FieldParams {
   float* dump_x;
   float* dump_s[10];
   float* dump_o[6];
+  // training forward of the tensor-core kernel: bf16 activation atoms, X atoms and LeakyReLU sign masks of every tile
+  // go to this workspace (layout.h: onerf_make_train_layout(use_voxel, n_rays * S)); null = inference
+  void* train_ws;
 };
 
 // removed-object mask: inside any box <=> lo <= A p + t <= hi (inclusive), utils/bbox_utils.py:158-207

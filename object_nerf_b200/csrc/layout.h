@@ -40,6 +40,11 @@ struct GemmDesc {
   int64_t wt_off;   // fp32 W^T [K][N], float offset into the blob
   int64_t bias_off; // fp32 [N] (for hoisted layers this bias is folded into ray_const and unused)
   int64_t img_off;  // bf16 stage images, BYTE offset into the blob; K/32 images of N*64 bytes
+  // backward (input-gradient chain, bwd_tc.cu): stage images of the TRANSPOSED hidden block of W,
+  //   B[n][k] = W[k][hid_col0 + n], n < hid_n (inputs taken from the previous hidden layer), k < N (outputs):
+  //   N/32 images of hid_n*64 bytes.  hid_n = 0: the layer has no hidden input (S0, O0).
+  int hid_n, hid_col0;     // hid_col0: first kernel-K column of the hidden block
+  int64_t bimg_off;
 };
 
 struct PackLayout {
@@ -55,8 +60,14 @@ struct PackLayout {
   int64_t h_ol0, h_ol2;         // [64][128] each
   int64_t b_sdir, b_odir, b_ol0, b_ol2;  // biases folded into ray_const
   int64_t fp32_floats;          // size of the fp32 section
+  // backward: images of the X blocks of the four X-fed layers (S0, S4, O0, O2), transposed, rows = X column
+  // (ONERF_DX_N rows, zero where a layer does not read the column), K = the layer's outputs:
+  //   per layer N/32 images of ONERF_DX_N*64 bytes, in the order S0, S4, O0, O2 (24 images)
+  int64_t ximg_off;
   int64_t total_bytes;
 };
+
+#define ONERF_DX_N 384
 
 static inline PackLayout onerf_make_layout(int use_voxel) {
   PackLayout L;
@@ -90,6 +101,84 @@ static inline PackLayout onerf_make_layout(int use_voxel) {
     L.g[i].img_off = bytes;
     bytes += (int64_t)(K[i] / 32) * N[i] * 64;
   }
+  // hidden input block of every layer (kernel-K columns): width and first column
+  const int hid_n[G_COUNT] = {0, 256, 256, 256, 256, 256, 256, 256, 256, 256, 0, 128, 128, 128, 128, 128};
+  const int hid_c[G_COUNT] = {0, 0, 0, 0, L.KX, 0, 0, 0, 0, 0, 0, 0, L.KO, 0, 0, 0};
+  for (int i = 0; i < G_COUNT; ++i) {
+    L.g[i].hid_n = hid_n[i];
+    L.g[i].hid_col0 = hid_c[i];
+    L.g[i].bimg_off = bytes;
+    bytes += (int64_t)(N[i] / 32) * hid_n[i] * 64;
+  }
+  L.ximg_off = bytes;
+  bytes += (int64_t)((256 + 256 + 128 + 128) / 32) * ONERF_DX_N * 64;
   L.total_bytes = bytes;
   return L;
 }
+
+// ---------------------------------------------------------------------------------------------------
+// Training dump ("atoms"): what the bf16 forward leaves behind for the tensor-core backward.
+// An atom is a [128 samples x 64 columns] bf16 block in the UMMA SWIZZLE_128B shared-memory layout
+// (row r at r*128 B, 16-byte chunk c of the row stored at chunk position c ^ (r & 7)); 16 KB.  The same image
+// serves as a K-major operand (K = columns: input-gradient GEMMs) and as an MN-major operand (K = samples:
+// weight-gradient GEMMs), so one bulk copy brings a ready-to-use tile into shared memory.
+//   activation slots: 0 = X (6 atoms voxel / 1 plain), 1..8 scene hidden 1..8, 9 scene final, 10 scene dir,
+//                     11..14 object hidden 1..4, 15 object final, 16 object dir    (same order as the fp32 dump)
+//   dZ slots        : gradient w.r.t. the pre-activation of the layer whose output is activation slot i + 1
+//   masks           : per tile ONERF_MASK_WORDS x 128 uint32: bit j of word w of row r = (output column > 0)
+// Slot-major: atom a of tile t of a slot lives at slot_off + (t * atoms + a) * 16 KB.
+// ---------------------------------------------------------------------------------------------------
+#define ONERF_ACT_SLOTS 17
+#define ONERF_DZ_SLOTS 16
+#define ONERF_MASK_WORDS 88      // scene hidden 8 x 8, scene dir 4, object hidden 4 x 4, object dir 4
+#define ONERF_ATOM_BYTES 16384
+
+struct TrainLayout {
+  int n_tiles;
+  int act_atoms[ONERF_ACT_SLOTS];
+  int dz_atoms[ONERF_DZ_SLOTS];
+  int64_t act_off[ONERF_ACT_SLOTS];   // byte offsets into the training workspace
+  int64_t dz_off[ONERF_DZ_SLOTS];
+  int64_t mask_off;
+  int64_t total_bytes;
+};
+
+static inline int onerf_mask_word0(int act_slot) {   // first mask word of the layer whose output is `act_slot`
+  if (act_slot >= 1 && act_slot <= 8) return (act_slot - 1) * 8;
+  if (act_slot == 10) return 64;
+  if (act_slot >= 11 && act_slot <= 14) return 68 + (act_slot - 11) * 4;
+  if (act_slot == 16) return 84;
+  return -1;   // final layers have no activation
+}
+
+static inline TrainLayout onerf_make_train_layout(int use_voxel, int64_t n_samples) {
+  TrainLayout T;
+  T.n_tiles = (int)((n_samples + 127) / 128);
+  const int aw[ONERF_ACT_SLOTS] = {use_voxel ? 6 : 1, 4, 4, 4, 4, 4, 4, 4, 4, 4, 2, 2, 2, 2, 2, 2, 1};
+  int64_t bytes = 0;
+  for (int i = 0; i < ONERF_ACT_SLOTS; ++i) {
+    T.act_atoms[i] = aw[i];
+    T.act_off[i] = bytes;
+    bytes += (int64_t)aw[i] * T.n_tiles * ONERF_ATOM_BYTES;
+  }
+  for (int i = 0; i < ONERF_DZ_SLOTS; ++i) {
+    T.dz_atoms[i] = aw[i + 1];
+    T.dz_off[i] = bytes;
+    bytes += (int64_t)aw[i + 1] * T.n_tiles * ONERF_ATOM_BYTES;
+  }
+  bytes += ONERF_ATOM_BYTES;   // the weight-gradient GEMM reads one atom past the 64-wide object-dir dZ slot
+  T.mask_off = bytes;
+  bytes += (int64_t)T.n_tiles * ONERF_MASK_WORDS * 128 * 4;
+  T.total_bytes = (bytes + 1023) & ~1023ll;
+  return T;
+}
+
+// Kernel-layout gradient buffer of one model (fp32), written by the tensor-core backward and mapped back to the
+// reference's [out,in] tensors by onerf_unpack_grads: per GEMM layer dW [N][K] (kernel-K columns) and db [N], then
+// the four heads.
+struct GradLayout {
+  int64_t w_off[G_COUNT], b_off[G_COUNT];
+  int64_t sigma_w, sigma_b, rgb_w, rgb_b, osigma_w, osigma_b, orgb_w, orgb_b;
+  int64_t total_floats;
+};
+GradLayout onerf_make_grad_layout(int use_voxel);

@@ -31,6 +31,21 @@ def new_seed() -> int:
     return int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
 
 
+def _on_device(fn):
+    """Run an ABI wrapper with the device of its first tensor argument current, so that kernels and the stream they are
+    enqueued on (torch.cuda.current_stream()) belong to the tensors' GPU even when another device is current."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        dev = next((a.device for a in args if isinstance(a, torch.Tensor)), None)
+        if dev is None or dev.type != "cuda" or dev.index is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return wrapped
+
+
 def _f32(t: torch.Tensor) -> torch.Tensor:
     if t.dtype != torch.float32:
         t = t.float()
@@ -76,9 +91,12 @@ def check_architecture(model, use_voxel: bool):
 
 
 def pack_weights(linears: Sequence, use_voxel: bool) -> torch.Tensor:
-    """Run the pack kernels; returns the packed blob (uint8 tensor, 1024-byte aligned)."""
+    """Run the pack kernel; returns the packed blob (uint8 tensor, 1024-byte aligned)."""
     lib = _lib.load()
     dev = linears[0][0].device
+    if dev.type == "cuda" and dev.index is not None and dev.index != torch.cuda.current_device():
+        with torch.cuda.device(dev):
+            return pack_weights(linears, use_voxel)
     ws = [_f32(w.detach()) for w, _ in linears]
     bs = [_f32(b.detach()) for _, b in linears]
     nbytes = lib.onerf_packed_weights_bytes(1 if use_voxel else 0)
@@ -93,19 +111,43 @@ def pack_weights(linears: Sequence, use_voxel: bool) -> torch.Tensor:
     return blob
 
 
-_pack_cache = {}
+_pack_cache = {}   # id(model) -> (weakref to the model, content fingerprint, blob)
 
 
-def packed_for(model, use_voxel: bool) -> torch.Tensor:
-    """Packed blob for an nn.Module, re-packed whenever any parameter was modified in place
-    (optimizer step) or replaced."""
+def _fingerprint(lin) -> tuple:
+    """Identity of the parameter CONTENT as far as it can be known without reading the device: storage address and
+    in-place version counter of every tensor.  Updates made through `.data` (torch_optimizer's RAdam / Ranger) do not bump
+    the version, which is why packed_for() never trusts this under autograd (see below) and exposes invalidate_packed()."""
+    return tuple((w.data_ptr(), w._version, b.data_ptr(), b._version) for w, b in lin)
+
+
+def invalidate_packed(model=None):
+    """Drop the cached packed weights of `model` (all models if None).  Call after modifying parameters in a way
+    autograd's version counter does not see (`p.data.copy_(...)`, `p.data.add_(...)`)."""
+    if model is None:
+        _pack_cache.clear()
+    else:
+        _pack_cache.pop(id(model), None)
+
+
+def packed_for(model, use_voxel: bool, fresh: Optional[bool] = None) -> torch.Tensor:
+    """Packed blob for an nn.Module.  Whenever gradients are enabled and a parameter requires grad (training: the
+    optimizer changes the weights between calls, possibly through `.data`) the weights are re-packed on EVERY call: one
+    kernel launch over 5 MB, far cheaper than a step.  Only inference calls (no_grad / frozen model) reuse a cached blob,
+    keyed on a weak reference to the module (a new module on a recycled id() never hits) plus the fingerprint above."""
     lin = check_architecture(model, use_voxel)
-    key = tuple((w.data_ptr(), w._version, b.data_ptr(), b._version) for w, b in lin)
+    if fresh is None:
+        fresh = torch.is_grad_enabled() and any(w.requires_grad or b.requires_grad for w, b in lin)
+    if fresh:
+        return pack_weights(lin, use_voxel)
+    key = (_fingerprint(lin), bool(use_voxel))
     hit = _pack_cache.get(id(model))
-    if hit is not None and hit[0] == key:
-        return hit[1]
+    if hit is not None and hit[0]() is model and hit[1] == key:
+        return hit[2]
     blob = pack_weights(lin, use_voxel)
-    _pack_cache[id(model)] = (key, blob)
+    import weakref
+    mid = id(model)
+    _pack_cache[mid] = (weakref.ref(model, lambda _r, mid=mid: _pack_cache.pop(mid, None)), key, blob)
     return blob
 
 
@@ -135,6 +177,7 @@ class GridBuffers:
 # ------------------------------------------------------------------------------------------------
 # stage kernels
 # ------------------------------------------------------------------------------------------------
+@_on_device
 def sample_coarse(rays, n_samples, use_disp=False, perturb=0.0, jitter=None, seed=0, out=None):
     rays = _f32(rays)
     n = rays.shape[0]
@@ -147,6 +190,7 @@ def sample_coarse(rays, n_samples, use_disp=False, perturb=0.0, jitter=None, see
     return z
 
 
+@_on_device
 def sample_pdf_merge(z_coarse, weights, n_importance, det, u=None, seed=0, out=None):
     z_coarse, weights = _f32(z_coarse), _f32(weights.detach())
     n, s = z_coarse.shape
@@ -160,6 +204,7 @@ def sample_pdf_merge(z_coarse, weights, n_importance, det, u=None, seed=0, out=N
     return out
 
 
+@_on_device
 def sample_pdf(bins, weights, n_importance, det, u=None, seed=0):
     bins, weights = _f32(bins), _f32(weights.detach())
     n, nb = bins.shape
@@ -172,6 +217,7 @@ def sample_pdf(bins, weights, n_importance, det, u=None, seed=0):
     return out
 
 
+@_on_device
 def encode(xyz, grid: Optional[GridBuffers]):
     xyz = _f32(xyz)
     n = xyz.shape[0]
@@ -182,6 +228,7 @@ def encode(xyz, grid: Optional[GridBuffers]):
     return scene, obj
 
 
+@_on_device
 def voxel_features(xyz, grid: GridBuffers):
     """Raw trilinear features (B,24) of the sparse voxel grid at xyz (no positional encoding)."""
     xyz = _f32(xyz).reshape(-1, 3)
@@ -191,6 +238,7 @@ def voxel_features(xyz, grid: GridBuffers):
     return out
 
 
+@_on_device
 def field(rays, z, packed, grid: Optional[GridBuffers], codes=None, code_row=None, want_scene=True,
           want_object=True, precision=None, xyz=None, mute_zero_rays=False, boxes=None, scene_out=None,
           obj_out=None, z_stride=None, out_stride=None, n_samples=None, activations=None):
@@ -238,6 +286,7 @@ def field(rays, z, packed, grid: Optional[GridBuffers], codes=None, code_row=Non
     return (scene_out if want_scene else None), (obj_out if want_object else None)
 
 
+@_on_device
 def composite(z, scene, obj, noise_std=0.0, white_back=False, is_eval=False, zero_last_delta=False,
               rays_in_bbox=False, frustum_bound_th=0.0, pass_through_mask=None, noise_scene=None,
               noise_obj=None, seed=0):
@@ -271,6 +320,7 @@ def composite(z, scene, obj, noise_std=0.0, white_back=False, is_eval=False, zer
     return out
 
 
+@_on_device
 def composite_multi(z_all, field_all, white_back=False, want_ids=False, want_unsorted=False):
     """z_all (n_obj, N, S), field_all (n_obj, N, S, 4) -> sorted-order outputs (N, n_obj*S)."""
     n_obj, n, s = z_all.shape
@@ -349,5 +399,6 @@ class RenderPlan:
 
     def run(self):
         """Enqueue the forward on the current stream; returns the reference's result dict (views of the plan's buffers)."""
-        _lib.check(_lib.load().onerf_render_rays_fwd(_lib.ctx(self.rays.device), C.byref(self.args), _lib.stream()))
+        with torch.cuda.device(self.rays.device):
+            _lib.check(_lib.load().onerf_render_rays_fwd(_lib.ctx(self.rays.device), C.byref(self.args), _lib.stream()))
         return {f"{k}_{typ}": v for typ, m in self.maps.items() for k, v in m.items()}

@@ -127,7 +127,7 @@ def _render_forward(cfg, rays, codes, keep=False):
 
     def one_pass(typ, z_vals, seed_off):
         model = cfg["models"][typ]
-        packed = engine.packed_for(model, use_voxel)
+        packed = engine.packed_for(model, use_voxel, fresh=cfg.get("fresh_pack"))
         scene, obj = engine.field(rays, z_vals, packed, grid, codes=codes if fi else None, want_scene=True,
                                   want_object=fi, precision=cfg["precision"])
         ns, no = rand.get(f"noise_scene_{typ}"), rand.get(f"noise_obj_{typ}")
@@ -188,15 +188,23 @@ def render_rays(models: Dict[str, Any], embeddings: Dict[str, Any], rays: torch.
         or (has_table and emb_xyz.embedding_space_ftr.weight.requires_grad))
     if not needs_grad:
         return _render_forward(cfg, rays, codes)[0]
-    if rays_in_bbox:
-        raise NotImplementedError("training with rays_in_bbox=True (weights swapped for sampling) is not built")
+    # Training.  rays_in_bbox only swaps which weights feed the (detached) importance sampling and the returned
+    # weights_* (models/rendering.py:228-229, :307): the gradients are unaffected.
     from . import backward
     cfg["has_table"], cfg["model_order"] = has_table, model_order
     params = ([emb_xyz.embedding_space_ftr.weight] if has_table else [])
     for typ in model_order:
         for w, b in engine.model_linears(models[typ]):
             params += [w, b]
-    tensors = backward.RenderRaysFn.apply(cfg, rays, codes, *params)
+    precision = cfg["precision"] or engine.default_precision()
+    if precision == "bf16" and has_table:
+        fn = backward.RenderRaysTcFn      # tcgen05 forward + backward
+    else:
+        # verification arithmetic (and the plain-PE model): fp32 forward AND backward, one function end to end
+        cfg["precision"] = "fp32"
+        cfg["fresh_pack"] = True          # training: never trust a cached blob (optimizers may write through .data)
+        fn = backward.RenderRaysFn
+    tensors = fn.apply(cfg, rays, codes, *params)
     keys = sorted(_result_keys(model_order, forward_instance))
     return dict(zip(keys, tensors))
 

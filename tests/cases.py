@@ -149,8 +149,9 @@ LOSS_CONF = dict(color_loss_weight=1.0, depth_loss_weight=0.1, opacity_loss_weig
 GRAD_SAMPLES = 256   # entries sampled per parameter tensor in the fixture
 
 
-def build_grad_case():
-    c = GRAD_CASE
+def build_grad_case(n_rays=None):
+    """n_rays=None: the fixture's case (tools/make_golden.py); other sizes reuse its seeds on more rays."""
+    c = GRAD_CASE if n_rays is None else dict(GRAD_CASE, n_rays=n_rays)
     inp = build_render_case(c)
     n = c["n_rays"]
     rng = np.random.default_rng(c["seed"] + 9)

@@ -33,7 +33,8 @@ def test_exports_every_declared_symbol(lib):
 
 
 def test_abi_version_and_sizes(lib):
-    assert lib.onerf_abi_version() == 1
+    from object_nerf_b200 import _lib
+    assert lib.onerf_abi_version() == _lib.ABI_VERSION == 2
     v, p = lib.onerf_packed_weights_bytes(1), lib.onerf_packed_weights_bytes(0)
     # fp32 section + bf16 stage images; see object_nerf_b200/csrc/layout.h
     assert v > p > 4 * 704840
@@ -94,9 +95,19 @@ def test_every_entry_point_rejects_a_null_context_with_a_message(lib):
         "onerf_colsum": (null, z, 4, 4, 4, z, z),
         "onerf_dir_encode": (null, z, 4, z, z),
         "onerf_encode_bwd": (null, None, z, z, 4, 4, z, z, 4, 0, 4, z, z),
+        "onerf_render_rays_bwd": (null, None, None, z),
+        "onerf_unpack_grads": (null, 1, z, None, None, z),
+        "onerf_bwd_chain": (null, 1, 1, z, z, 128, z, z, z),
+        "onerf_bwd_wgrad": (null, 1, 1, z, 128, z, z),
+        "onerf_bwd_colsums": (null, 1, 1, z, 128, z, z, z, z),
+        "onerf_bwd_raysums": (null, 1, 1, z, 2, 64, z, z),
+        "onerf_bwd_dx": (null, 1, z, z, z, z, 2, 64, None, z, z),
+        "onerf_code_gather": (null, z, z, 4, 64, z, z),
+        "onerf_code_scatter_add": (null, z, z, 4, 64, z, z),
     }
     helpers = {"onerf_abi_version", "onerf_last_error", "onerf_ctx_create", "onerf_ctx_destroy", "onerf_ctx_launch_count",
-               "onerf_packed_weights_bytes", "onerf_render_rays_workspace_bytes", "onerf_total_loss_workspace_bytes"}
+               "onerf_packed_weights_bytes", "onerf_render_rays_workspace_bytes", "onerf_total_loss_workspace_bytes",
+               "onerf_field_train_bytes", "onerf_train_workspace_bytes", "onerf_grad_buffer_floats"}
     assert set(calls) | helpers == set(_lib.EXPORTS)
     for name, args in calls.items():
         rc = getattr(lib, name)(*args)
@@ -104,3 +115,8 @@ def test_every_entry_point_rejects_a_null_context_with_a_message(lib):
         assert len(lib.onerf_last_error()) > 0, name
     assert lib.onerf_render_rays_workspace_bytes(1024, 64, 64) >= 1024 * (448 * 4 + 2 * 128 * 16)
     assert lib.onerf_total_loss_workspace_bytes() >= 16 * 8
+    # training workspace: 104 operand tiles of 16 KB + 45 KB of masks per 128 samples, for both passes
+    per_tile = 104 * 16384 + 88 * 128 * 4
+    assert lib.onerf_field_train_bytes(1, 128 * 10) >= 10 * per_tile
+    assert lib.onerf_train_workspace_bytes(1, 2048, 64, 64) >= (1024 + 2048) * per_tile
+    assert lib.onerf_grad_buffer_floats(1) >= 891208 - 27 * 192 - 64 * 256
