@@ -367,10 +367,13 @@ extern "C" int onerf_gemm(onerf_ctx* ctx, const float* A, int lda, int trans_a, 
   const int gx = (N + GB - 1) / GB, gy = (M + GB - 1) / GB;
   // split the reduction when the output grid alone cannot fill the machine (weight gradients: K = samples)
   int splits = 1;
-  if (K >= 4096) {
+  if (K >= 256 && gx * gy < 2 * ctx->num_sms) {
     const int want = (4 * ctx->num_sms + gx * gy - 1) / (gx * gy);
     splits = want < 1 ? 1 : (want > 256 ? 256 : want);
-    while (splits > 1 && K / splits < 512) --splits;
+    // long reductions (weight gradients over samples) keep >= 512 rows per CTA; short ones (per-ray sums, K = rays of
+    // one batch) would otherwise run on one or two CTAs: let them go down to 32 rows
+    const int min_k = K >= 4096 ? 512 : 32;
+    while (splits > 1 && K / splits < min_k) --splits;
   }
   int kps = ((K + splits - 1) / splits + GK - 1) / GK * GK;
   splits = (K + kps - 1) / kps;

@@ -24,8 +24,11 @@ batch = {"rgbs": torch.rand(n, 3, device=dev), "depths": torch.rand(n, device=de
          "instance_mask_weight": torch.where(torch.rand(n, device=dev) < 0.5, 1.0, 0.05)}
 ptm = torch.rand(n, 1, device=dev) < 0.5
 params = [p for m in models.values() for p in m.parameters()] + list(lib.parameters()) + list(emb.parameters())
-opt = torch.optim.Adam(params, lr=1e-3)
-precision = os.environ.get("ONERF_PRECISION", "fp32")
+opt = torch.optim.Adam(params, lr=1e-3, fused=True)
+precision = os.environ.get("ONERF_PRECISION", "bf16")
+from object_nerf_b200.losses import TotalLoss
+loss_fn = TotalLoss({k: v for k, v in cases.LOSS_CONF.items()})
+STEPS = int(os.environ.get("TRAIN_STEPS", 10))
 
 def step():
     opt.zero_grad(set_to_none=True)
@@ -35,7 +38,7 @@ def step():
     out = render_rays(models, {"xyz": emb, "dir": Embedding(3, 4)}, rays, N_samples=64, perturb=1.0, noise_std=1.0,
                       N_importance=64, embedding_instance=codes, frustum_bound_th=0.025, pass_through_mask=ptm,
                       is_eval=False, precision=precision)
-    loss = cases.total_loss(out, batch)
+    loss, _ = loss_fn(out, batch)
     e[1].record()
     loss.backward()
     e[2].record()
@@ -44,9 +47,9 @@ def step():
     torch.cuda.synchronize()
     return loss.item(), [e[i].elapsed_time(e[i + 1]) for i in range(3)]
 
-for _ in range(2):
+for _ in range(3):
     step()
-ts = [step() for _ in range(5)]
+ts = [step() for _ in range(STEPS)]
 fw = np.mean([t[1][0] for t in ts]); bw = np.mean([t[1][1] for t in ts]); ad = np.mean([t[1][2] for t in ts])
 print(f"train step, {n} rays, forward precision {precision}: forward+loss {fw:.1f} ms, backward {bw:.1f} ms, adam {ad:.1f} ms, "
       f"total {fw+bw+ad:.1f} ms = {n/(fw+bw+ad)*1e3:.0f} rays/s; losses {[round(t[0],4) for t in ts]}")
