@@ -104,10 +104,12 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # synthetic scene (no datasets / checkpoints offline: SURVEY.md §8d)
 # ------------------------------------------------------------------------------------------------
-def build_scene():
+def build_scene(device=None):
     from object_nerf_b200 import synthetic as S
-    wc = S.make_weights(0, True, sigma_gain=8.0, sigma_bias=1.0)
-    wf = S.make_weights(1000, True, sigma_gain=8.0, sigma_bias=1.0)
+    # density heads sharpened and colour heads scaled so that the render has structure (opacity and colours spread over
+    # their range); default nn.Linear init renders a flat grey on which every renderer agrees trivially
+    wc = S.make_weights(0, True, sigma_gain=8.0, sigma_bias=1.0, rgb_gain=24.0)
+    wf = S.make_weights(1000, True, sigma_gain=8.0, sigma_bias=1.0, rgb_gain=24.0)
     grid = S.make_grid(seed=5, shape=(42, 42, 22), occupancy=0.6, voxel_size=0.05, n_rows=800000)
     rays = S.pinhole_rays(H, W)                      # (307200, 8), pinhole 640x480, unit directions
     code_table = S.make_codes(2)

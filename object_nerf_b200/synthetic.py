@@ -38,10 +38,12 @@ def layer_dims(use_voxel: bool = True):
     return dims
 
 
-def make_weights(seed: int, use_voxel: bool = True, sigma_gain: float = 1.0, sigma_bias: float = 0.0):
+def make_weights(seed: int, use_voxel: bool = True, sigma_gain: float = 1.0, sigma_bias: float = 0.0,
+                 rgb_gain: float = 1.0):
     """nn.Linear-style init U(-1/sqrt(fan_in), 1/sqrt(fan_in)) for W and b, in a fixed layer order.
     sigma_gain / sigma_bias sharpen the density heads so that weights / PDFs are not degenerate
-    (random init gives sigma ~ 0, i.e. a transparent scene)."""
+    (random init gives sigma ~ 0, i.e. a transparent scene); rgb_gain scales the colour heads (random init gives a flat
+    grey: sigmoid of ~0 everywhere, on which any two renderers agree trivially)."""
     rng = np.random.default_rng(seed)
     w = {}
     for name, k, n in layer_dims(use_voxel):
@@ -51,6 +53,9 @@ def make_weights(seed: int, use_voxel: bool = True, sigma_gain: float = 1.0, sig
         if name.endswith(".sigma"):
             W = (W * sigma_gain).astype(np.float32)
             b = (b * sigma_gain + sigma_bias).astype(np.float32)
+        if name.endswith(".rgb") and rgb_gain != 1.0:
+            W = (W * rgb_gain).astype(np.float32)
+            b = (b * rgb_gain).astype(np.float32)
         w[name] = (torch.from_numpy(W), torch.from_numpy(b))
     return w
 
