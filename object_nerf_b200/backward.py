@@ -376,12 +376,16 @@ class RenderRaysTcFn(torch.autograd.Function):
         ctx.keys = keys
         tensors = tuple(out[k] for k in keys)
         ctx.mark_non_differentiable(*[t for k, t in zip(keys, tensors) if k.startswith(("weights_", "z_vals_"))])
+        # the backward reads the forward's maps (depths, scene depth) through the raw pointers in `a`: keep the tensors
+        # alive (a caller may drop the result dict right after the loss; non-differentiable outputs have no other owner)
+        ctx.save_for_backward(*tensors)
         return tensors
 
     @staticmethod
     def backward(ctx, *gouts):
         lib = _lib.load()
         a, cfg = ctx.args, ctx.cfg
+        _alive = ctx.saved_tensors  # noqa: F841
         dev = ctx.keep[0].device
         g = {k: (v.contiguous().float() if v is not None else None) for k, v in zip(ctx.keys, gouts)}
         b = _lib.RenderBwdArgs()

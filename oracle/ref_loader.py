@@ -76,6 +76,10 @@ def install(root=REF_BUILD, cuda_noop=None):
         base = torch.stack(torch.meshgrid([xs, ys], indexing="ij"), dim=-1)
         return base.permute(1, 0, 2).unsqueeze(0)
     k.create_meshgrid = create_meshgrid  # datasets/ray_utils.py:2,17
+    k.__path__ = []
+    kl = _stub("kornia.losses")
+    kl.ssim = lambda *a, **k: (_ for _ in ()).throw(NotImplementedError("kornia.losses.ssim stub"))  # utils/metrics.py:2
+    k.losses = kl
     o3d = _stub("open3d")
     io = _stub("open3d.io")
     io.read_point_cloud = lambda p: _FakePcd(_PCD_REGISTRY[p])
@@ -150,6 +154,13 @@ def install_lightning_shim():
         def save_hyperparameters(self, *a, **k):
             pass
 
+    def load_from_checkpoint(cls, checkpoint_path, map_location=None, **kwargs):
+        """pytorch_lightning 1.5 semantics for the one call the reference makes (editable_renderer.py:76)."""
+        obj = cls(**kwargs)
+        ck = torch.load(checkpoint_path, map_location=map_location or "cpu", weights_only=False)
+        obj.load_state_dict(ck["state_dict"], strict=True)
+        return obj
+    LightningModule.load_from_checkpoint = classmethod(load_from_checkpoint)
     pl.LightningModule = LightningModule
     pl.Trainer = type("Trainer", (), {"__init__": lambda self, *a, **k: None})
     cb = _stub("pytorch_lightning.callbacks")
