@@ -224,6 +224,47 @@ size_t onerf_render_rays_workspace_bytes(int n_rays, int n_samples, int n_import
 int onerf_render_rays_fwd(onerf_ctx* ctx, const onerf_render_args* args, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Whole forward of render_rays_multi() in ONE call, render_tools/multi_rendering.py:160-325 (the editing path of
+ * EditableRenderer.scene_inference / render_edit, editable_renderer.py:125-140, 272-287; inference only, as in the
+ * reference).  Ray set k is rendered with the scene branch if obj_ids[k] == 0 (removed-object boxes applied on the device)
+ * or with the object branch and code_table[obj_ids[k]] otherwise; the sets are composited jointly (stable depth sort).
+ * `_host` arrays are read on the host at call time.  Only enqueues kernels on `stream`: CUDA-graph capturable.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct onerf_render_multi_maps {   /* result dict of one pass, T = n_obj * samples of the pass */
+  float* weights;          /* (N,T) in jointly sorted order */
+  float* opacity;          /* (N,) */
+  float* z_vals;           /* (N,T) sorted depths */
+  float* rgb;              /* (N,3) */
+  float* depth;            /* (N,) */
+  float* obj_ids;          /* (N,T) list position of each sorted sample ("obj_ids_coarse"); coarse pass only */
+} onerf_render_multi_maps;
+
+typedef struct onerf_render_multi_args {
+  const float* const* rays_list_host; /* n_obj DEVICE pointers to (N,8) ray sets, the array itself in host memory */
+  const int* obj_ids_host;            /* n_obj instance ids (host) */
+  int n_obj, n_rays, n_samples, n_importance;
+  const onerf_grid* grid;             /* required (the reference's editing path assumes the voxel embedding) */
+  const void* packed_coarse;
+  const void* packed_fine;            /* required iff n_importance > 0 */
+  const float* code_table;            /* (n_codes,64) CodeLibrary.embedding_instance.weight */
+  int n_codes;
+  int precision;                      /* onerf_precision */
+  int use_disp;
+  float perturb;                      /* 0: deterministic importance samples (what EditableRenderer passes) */
+  uint64_t seed;
+  int white_back;
+  const float* boxes;                 /* (n_boxes,18) removed-object boxes (see onerf_field_args), or NULL */
+  int n_boxes;
+  onerf_render_multi_maps coarse;
+  onerf_render_multi_maps fine;       /* written iff n_importance > 0 */
+  void* workspace;                    /* >= onerf_render_multi_workspace_bytes(...) bytes, 256-byte aligned */
+  size_t workspace_bytes;
+} onerf_render_multi_args;
+
+size_t onerf_render_multi_workspace_bytes(int n_rays, int n_obj, int n_samples, int n_importance);
+int onerf_render_multi_fwd(onerf_ctx* ctx, const onerf_render_multi_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Rays: the two host steps directly in front of the path, on the device.
  * `_host` pointers are read on the host at call time (a 3x4 pose, one box), everything else is device memory.
  * ------------------------------------------------------------------------------------------- */

@@ -32,7 +32,7 @@ EXPORTS = [
     "onerf_dir_encode", "onerf_encode_bwd",
     "onerf_field_train_bytes", "onerf_train_workspace_bytes", "onerf_render_rays_bwd", "onerf_grad_buffer_floats",
     "onerf_unpack_grads", "onerf_bwd_chain", "onerf_bwd_wgrad", "onerf_bwd_colsums", "onerf_bwd_raysums", "onerf_bwd_dx",
-    "onerf_code_gather", "onerf_code_scatter_add",
+    "onerf_code_gather", "onerf_code_scatter_add", "onerf_render_multi_workspace_bytes", "onerf_render_multi_fwd",
 ]
 
 _p = C.c_void_p
@@ -97,6 +97,20 @@ class RenderArgs(C.Structure):
         ("zero_last_delta", C.c_int), ("rays_in_bbox", C.c_int), ("frustum_bound_th", C.c_float),
         ("pass_through_mask", _p), ("coarse", RenderMaps), ("fine", RenderMaps), ("workspace", _p),
         ("workspace_bytes", C.c_size_t), ("train_ws", _p), ("train_ws_bytes", C.c_size_t),
+    ]
+
+
+class RenderMultiMaps(C.Structure):
+    _fields_ = [("weights", _p), ("opacity", _p), ("z_vals", _p), ("rgb", _p), ("depth", _p), ("obj_ids", _p)]
+
+
+class RenderMultiArgs(C.Structure):
+    _fields_ = [
+        ("rays_list_host", C.POINTER(_p)), ("obj_ids_host", C.POINTER(C.c_int)), ("n_obj", C.c_int), ("n_rays", C.c_int),
+        ("n_samples", C.c_int), ("n_importance", C.c_int), ("grid", C.POINTER(Grid)), ("packed_coarse", _p),
+        ("packed_fine", _p), ("code_table", _p), ("n_codes", C.c_int), ("precision", C.c_int), ("use_disp", C.c_int),
+        ("perturb", C.c_float), ("seed", C.c_uint64), ("white_back", C.c_int), ("boxes", _p), ("n_boxes", C.c_int),
+        ("coarse", RenderMultiMaps), ("fine", RenderMultiMaps), ("workspace", _p), ("workspace_bytes", C.c_size_t),
     ]
 
 
@@ -187,6 +201,9 @@ def load() -> C.CDLL:
         lib.onerf_bwd_dx.argtypes = [_p, C.c_int, _p, _p, _p, _p, C.c_int, C.c_int, C.POINTER(Grid), _p, _p]
         lib.onerf_code_gather.argtypes = [_p, _p, _p, C.c_int, C.c_int, _p, _p]
         lib.onerf_code_scatter_add.argtypes = [_p, _p, _p, C.c_int, C.c_int, _p, _p]
+        lib.onerf_render_multi_workspace_bytes.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
+        lib.onerf_render_multi_workspace_bytes.restype = C.c_size_t
+        lib.onerf_render_multi_fwd.argtypes = [_p, C.POINTER(RenderMultiArgs), _p]
         if lib.onerf_abi_version() != ABI_VERSION:
             raise RuntimeError("libonerf_sm100.so ABI version mismatch")
         _lib = lib

@@ -199,3 +199,98 @@ extern "C" int onerf_render_rays_fwd(onerf_ctx* ctx, const onerf_render_args* a,
   return render_pass(ctx, a, a->packed_fine, a->fine.z_vals, SF, a->fine, a->noise_scene_fine, a->noise_obj_fine, a->seed + 3,
                      ray_const, scene_f, obj_f, tl_f, stream);
 }
+
+// ------------------------------------------------------------------------------------------------
+// render_rays_multi() forward as one call (render_tools/multi_rendering.py:160-325): per ray set coarse depths and a
+// one-branch field evaluation (scene branch + removed-object boxes for id 0, object branch with the id's code row
+// otherwise, zero-length rays muted), joint stable depth sort + compositing, per-set importance resampling, fine pass.
+// Same kernels, order and arguments as object_nerf_b200/multi_rendering.py::render_rays_multi (staged route).
+// ------------------------------------------------------------------------------------------------
+extern "C" size_t onerf_render_multi_workspace_bytes(int n_rays, int n_obj, int n_samples, int n_importance) {
+  if (n_rays < 0 || n_obj < 1 || n_samples < 1 || n_importance < 0) return 0;
+  const size_t sf = (size_t)n_samples + (size_t)n_importance, no = (size_t)n_obj, n = (size_t)n_rays;
+  return align256(n * ONERF_RAY_CONST_FLOATS * sizeof(float)) +          // per-ray hoisted terms (one set at a time)
+         align256(no * n * n_samples * sizeof(float)) +                  // coarse depths of every set
+         align256(no * n * sf * sizeof(float)) +                         // fine depths
+         align256(no * n * sf * 4 * sizeof(float)) +                     // fields (rgb, sigma) of every set
+         align256(no * n * n_samples * sizeof(float));                   // per-set coarse weights in sample order
+}
+
+static int multi_fields(onerf_ctx* ctx, const onerf_render_multi_args* a, const void* packed, const float* z_all, int S,
+                        float* field_all, float* ray_const, void* stream) {
+  for (int i = 0; i < a->n_obj; ++i) {
+    const int id = a->obj_ids_host[i];
+    onerf_field_args f;
+    memset(&f, 0, sizeof(f));
+    f.rays = a->rays_list_host[i];
+    f.z = z_all + (size_t)i * a->n_rays * S;
+    f.z_stride = S;
+    f.code_row = id > 0 ? a->code_table + (size_t)id * ONERF_NCODE : nullptr;
+    f.n_rays = a->n_rays; f.n_samples = S;
+    f.grid = a->grid; f.packed = packed;
+    f.want_scene = id > 0 ? 0 : 1; f.want_object = id > 0 ? 1 : 0;
+    f.precision = a->precision;
+    f.mute_zero_rays = 1;
+    if (id == 0) { f.boxes = a->boxes; f.n_boxes = a->n_boxes; }
+    float* out = field_all + (size_t)i * a->n_rays * S * 4;
+    f.scene_out = id > 0 ? nullptr : out;
+    f.obj_out = id > 0 ? out : nullptr;
+    f.out_stride = S;
+    f.ray_const = ray_const;
+    int rc = onerf_field_fwd(ctx, &f, stream);
+    if (rc != ONERF_OK) return rc;
+  }
+  return ONERF_OK;
+}
+
+extern "C" int onerf_render_multi_fwd(onerf_ctx* ctx, const onerf_render_multi_args* a, void* stream) {
+  ONERF_CHECK_ARG(ctx && a, "null argument");
+  ONERF_CHECK_ARG(a->rays_list_host && a->obj_ids_host && a->packed_coarse && a->grid && a->code_table, "null input");
+  ONERF_CHECK_ARG(a->n_rays >= 0 && a->n_obj >= 1 && a->n_samples >= 2 && a->n_importance >= 0, "bad shape");
+  ONERF_UNSUPPORTED((size_t)a->n_obj * (a->n_samples + a->n_importance) > 4096, "n_obj * samples > 4096");
+  ONERF_CHECK_ARG(a->n_importance == 0 || a->packed_fine, "n_importance > 0 needs packed_fine");
+  ONERF_CHECK_ARG(a->n_boxes == 0 || a->boxes, "n_boxes > 0 with null boxes");
+  for (int i = 0; i < a->n_obj; ++i) {
+    ONERF_CHECK_ARG(a->rays_list_host[i], "null ray set");
+    ONERF_CHECK_ARG(a->obj_ids_host[i] >= 0 && a->obj_ids_host[i] < a->n_codes, "object id outside the code table");
+  }
+  const onerf_render_multi_maps& c = a->coarse;
+  ONERF_CHECK_ARG(c.weights && c.opacity && c.z_vals && c.rgb && c.depth && c.obj_ids, "null coarse output");
+  if (a->n_importance > 0)
+    ONERF_CHECK_ARG(a->fine.weights && a->fine.opacity && a->fine.z_vals && a->fine.rgb && a->fine.depth, "null fine output");
+  const size_t need = onerf_render_multi_workspace_bytes(a->n_rays, a->n_obj, a->n_samples, a->n_importance);
+  ONERF_CHECK_ARG(a->workspace && (reinterpret_cast<uintptr_t>(a->workspace) & 255u) == 0, "workspace null or not 256-byte aligned");
+  if (a->workspace_bytes < need) {
+    onerf_set_error("onerf_render_multi_fwd: workspace too small (%zu < %zu)", a->workspace_bytes, need);
+    return ONERF_ERR_WORKSPACE;
+  }
+  if (a->n_rays == 0) return ONERF_OK;
+  const int S = a->n_samples, SF = a->n_samples + a->n_importance, N = a->n_rays, NO = a->n_obj;
+  char* ws = reinterpret_cast<char*>(a->workspace);
+  auto take = [&](size_t bytes) { float* p = reinterpret_cast<float*>(ws); ws += align256(bytes); return p; };
+  float* ray_const = take((size_t)N * ONERF_RAY_CONST_FLOATS * sizeof(float));
+  float* z_all = take((size_t)NO * N * S * sizeof(float));
+  float* z_fine = take((size_t)NO * N * SF * sizeof(float));
+  float* field_all = take((size_t)NO * N * SF * 4 * sizeof(float));
+  float* w_unsorted = take((size_t)NO * N * S * sizeof(float));
+  int rc;
+  for (int i = 0; i < NO; ++i) {   // multi_rendering.py:196-213: coarse depths are never jittered on this path
+    rc = onerf_sample_coarse(ctx, a->rays_list_host[i], N, S, a->use_disp, 0.0f, nullptr, 0, z_all + (size_t)i * N * S, stream);
+    if (rc != ONERF_OK) return rc;
+  }
+  rc = multi_fields(ctx, a, a->packed_coarse, z_all, S, field_all, ray_const, stream);
+  if (rc != ONERF_OK) return rc;
+  rc = onerf_composite_multi(ctx, z_all, field_all, N, NO, S, a->white_back, c.z_vals, c.weights, c.obj_ids,
+                             a->n_importance > 0 ? w_unsorted : nullptr, c.opacity, c.rgb, c.depth, stream);
+  if (rc != ONERF_OK || a->n_importance == 0) return rc;
+  const int det = a->perturb == 0.0f ? 1 : 0;
+  for (int i = 0; i < NO; ++i) {
+    rc = onerf_sample_pdf_merge(ctx, z_all + (size_t)i * N * S, w_unsorted + (size_t)i * N * S, N, S, a->n_importance, det, nullptr,
+                                det ? 0 : a->seed + (uint64_t)i, z_fine + (size_t)i * N * SF, stream);
+    if (rc != ONERF_OK) return rc;
+  }
+  rc = multi_fields(ctx, a, a->packed_fine, z_fine, SF, field_all, ray_const, stream);
+  if (rc != ONERF_OK) return rc;
+  return onerf_composite_multi(ctx, z_fine, field_all, N, NO, SF, a->white_back, a->fine.z_vals, a->fine.weights, nullptr, nullptr,
+                               a->fine.opacity, a->fine.rgb, a->fine.depth, stream);
+}

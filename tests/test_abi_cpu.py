@@ -104,10 +104,12 @@ def test_every_entry_point_rejects_a_null_context_with_a_message(lib):
         "onerf_bwd_dx": (null, 1, z, z, z, z, 2, 64, None, z, z),
         "onerf_code_gather": (null, z, z, 4, 64, z, z),
         "onerf_code_scatter_add": (null, z, z, 4, 64, z, z),
+        "onerf_render_multi_fwd": (null, None, z),
     }
     helpers = {"onerf_abi_version", "onerf_last_error", "onerf_ctx_create", "onerf_ctx_destroy", "onerf_ctx_launch_count",
                "onerf_packed_weights_bytes", "onerf_render_rays_workspace_bytes", "onerf_total_loss_workspace_bytes",
-               "onerf_field_train_bytes", "onerf_train_workspace_bytes", "onerf_grad_buffer_floats"}
+               "onerf_field_train_bytes", "onerf_train_workspace_bytes", "onerf_grad_buffer_floats",
+               "onerf_render_multi_workspace_bytes"}
     assert set(calls) | helpers == set(_lib.EXPORTS)
     for name, args in calls.items():
         rc = getattr(lib, name)(*args)

@@ -277,7 +277,7 @@ def test_render_rays_matches_reference_golden(golden, name, precision):
                 close(out[k], gold[k], 3e-2, k)
 
 
-def _run_multi_case(c, precision):
+def _run_multi_case(c, precision, staged=False):
     from object_nerf_b200 import Embedding
     from object_nerf_b200.multi_rendering import render_rays_multi
     inp = cases.build_multi_case(c)
@@ -297,7 +297,19 @@ def _run_multi_case(c, precision):
     return render_rays_multi(models, {"xyz": emb, "dir": Embedding(3, 4)}, helpers.CodeLib(inp["code_table"]).to(DEV),
                              [r.to(DEV) for r in inp["rays_list"]], c["obj_ids"], N_samples=c["n_samples"],
                              N_importance=c["n_importance"], white_back=c["white_back"],
-                             background_skip_bbox=boxes, precision=precision)
+                             background_skip_bbox=boxes, precision=precision, _staged=staged)
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("name", list(cases.MULTI_CASES))
+def test_render_multi_one_call_is_bit_identical_to_staged_route(name, precision):
+    """onerf_render_multi_fwd (the whole render_rays_multi forward in one C call) against the same kernels driven stage by
+    stage from Python."""
+    c = cases.MULTI_CASES[name]
+    one, staged = _run_multi_case(c, precision), _run_multi_case(c, precision, staged=True)
+    assert set(one) == set(staged)
+    for k in one:
+        assert torch.equal(one[k], staged[k]), k
 
 
 @pytest.mark.parametrize("precision", PRECISIONS)
