@@ -280,7 +280,36 @@ def gpu_torch_baseline(sc, dev):
                 e1.record()
                 torch.cuda.synchronize()
                 res[f"rays_per_s_{n}_{'tf32' if tf32 else 'fp32'}"] = n * reps / (e0.elapsed_time(e1) * 1e-3)
+        # ---- the reference's training step (train.py:147-180 with its own models / loss / autograd) on the same GPU ----
+        from oracle import ref_loader as R
+        from models.code_library import CodeLibrary
+        from models.losses import TotalLoss
+        from models.rendering import render_rays as ref_render_rays
+        models, emb = R.ref_render_setup(sc["weights"], sc["grid"], dev)
+        for m in models.values():
+            m.train()
+        lib = CodeLibrary(R.default_model_config()).to(dev)
+        loss_fn = TotalLoss(R.AttrDict(LOSS_CONF))
+        params = [p for m in models.values() for p in m.parameters()] + list(lib.parameters()) + list(emb["xyz"].parameters())
+        opt = torch.optim.Adam(params, lr=1e-3, eps=1e-8)
+        batch = {k: v.to(dev) for k, v in train_batches(1, 0)[0].items()}
+
+        def ref_step():
+            opt.zero_grad(set_to_none=True)
+            codes = lib(batch)["embedding_instance"]
+            out = ref_render_rays(models, emb, batch["rays"], N_samples=N_SAMPLES, use_disp=False, perturb=1.0, noise_std=1.0,
+                                  N_importance=N_IMPORTANCE, chunk=32768, white_back=False, embedding_instance=codes,
+                                  frustum_bound_th=0.025, pass_through_mask=batch["pass_through_mask"], is_eval=False)
+            loss, _ = loss_fn(out, batch)
+            loss.backward()
+            opt.step()
+
+        for tf32 in (False, True):
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            torch.backends.cudnn.allow_tf32 = tf32
+            res[f"train_rays_per_s_{TRAIN_RAYS}_{'tf32' if tf32 else 'fp32'}"] = TRAIN_RAYS / (event_ms(ref_step, reps=5) * 1e-3)
         torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = False
         return res
     except Exception as ex:  # a baseline must never take the product line down
         return {"unavailable": f"{type(ex).__name__}: {ex}"[:200]}

@@ -82,7 +82,12 @@ class EmbeddingVoxel(nn.Module):
         return engine.GridBuffers.from_module(self)
 
     def forward(self, xyz):
-        scene, obj = engine.encode(xyz.reshape(-1, 3), self.grid_buffers())
+        """(B,3) -> (scene input (B,271), object voxel input (B,104)), reference :325-329.  The returned tensors remember
+        the positions and grid they were encoded from, so that ObjectNeRF.forward(..., sigma_only=True) on them (the
+        mesh-extraction call pattern, tools/extract_mesh.py:83-109) runs the fused encode + MLP kernel on the positions."""
+        pts = xyz.reshape(-1, 3)
+        scene, obj = engine.encode(pts, engine.GridBuffers.from_module(self))
+        scene._onerf_src = obj._onerf_src = (pts, self)
         return scene, obj
 
     # ---- cold path at epoch boundaries: grid maintenance (reference :202-302, called from train.py:140-145) ----

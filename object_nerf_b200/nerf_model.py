@@ -69,9 +69,28 @@ class ObjectNeRF(nn.Module):
         self.inst_dir_encoding = _act_linear(inst_W + self.in_channels_dir, inst_W // 2, act)
         self.inst_rgb = nn.Sequential(nn.Linear(inst_W // 2, 3), nn.Sigmoid())
 
-    def forward(self, inputs, sigma_only=False):
-        raise NotImplementedError(
-            "ObjectNeRF here is a weight container; the MLP runs fused inside render_rays()/render_rays_multi() "
-            "(per-embedding evaluation for tools/extract_mesh.py is a SURVEY.md §8f 'next' row)")
+    def _density(self, inputs, obj_code):
+        src = getattr(inputs.get("emb_xyz"), "_onerf_src", None) if isinstance(inputs, dict) else None
+        if src is None:
+            raise NotImplementedError(
+                "ObjectNeRF is a weight container: the MLP runs fused with the encoding inside render_rays() / "
+                "render_rays_multi() / query_sigma().  forward(..., sigma_only=True) is supported on inputs produced by "
+                "EmbeddingVoxel.forward(xyz) (they carry their positions); arbitrary pre-embedded features are not.")
+        from . import rendering
+        pts, emb = src
+        return rendering.query_sigma(self, emb, pts, obj_code=obj_code)[:, None]
 
-    forward_instance = forward
+    def forward(self, inputs, sigma_only=False):
+        """Reference :97-121.  Only the density query (`sigma_only=True`: tools/extract_mesh.py:104-107, the voxel pruning
+        of embedding_helper.py:219-225) is served here, through the fused kernel; colours come from render_rays()."""
+        if not sigma_only:
+            raise NotImplementedError("per-sample colours are produced inside render_rays() / render_rays_multi()")
+        return {"sigma": self._density(inputs, None)}
+
+    def forward_instance(self, inputs, sigma_only=False):
+        """Reference :123-152, density only (tools/extract_mesh.py:95-103): inputs["obj_code"] holds one code per point,
+        all rows equal (the reference looks the same id up for every point)."""
+        if not sigma_only:
+            raise NotImplementedError("per-sample colours are produced inside render_rays() / render_rays_multi()")
+        code = inputs["obj_code"]
+        return {"inst_sigma": self._density(inputs, code[0] if code.dim() == 2 else code)}

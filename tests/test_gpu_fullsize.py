@@ -103,3 +103,65 @@ def test_training_mode_device_rng_statistics(scene):
     base = near * (1 - t) + far * t
     mid = 0.5 * (base[:, 1:] + base[:, :-1])
     assert (z[:, 1:-1] >= mid[:, :-1] - 1e-5).all() and (z[:, 1:-1] <= mid[:, 1:] + 1e-5).all()
+
+
+# ------------------------------------------------------------------------------------------------
+# parity at the benchmark configuration, directly against the reference (oracle/_ref: the unmodified reference
+# byte-compiled at build time) or, where that is absent, the oracle port pinned to it
+# ------------------------------------------------------------------------------------------------
+def test_bench_scene_render_matches_reference_directly(scene):
+    """2 048 rays of the bench frame (the bench's own scene, weights and sample counts), bf16 and fp32, against the
+    reference's render_rays on the host.  Tolerances are the measured errors plus margin (profiles/r02_parity.md)."""
+    sc = bench.build_scene()
+    kind, ref_render = bench.reference_renderer(sc)
+    sel = torch.linspace(0, bench.N_RAYS - 1, 2048).long()
+    want = ref_render(sc["rays"][sel], sc["codes"][sel])
+    sub = dict(scene, rays=scene["rays"][sel.to(DEV)].contiguous(), codes=scene["codes"][sel.to(DEV)].contiguous())
+    assert want["rgb_fine"].std().item() > 0.05, "the bench scene must have structure for this test to mean anything"
+    tol = {"fp32": dict(rgb=2e-5, depth=2e-5, inst=5e-5, psnr=100.0), "bf16": dict(rgb=3e-3, depth=5e-3, inst=1e-2, psnr=65.0)}
+    for precision in ("fp32", "bf16"):
+        got = {k: v.cpu() for k, v in render(sub, slice(None), precision).items()}
+        t = tol[precision]
+        assert helpers.psnr(got["rgb_fine"], want["rgb_fine"]) > t["psnr"], (precision, helpers.psnr(got["rgb_fine"], want["rgb_fine"]))
+        for k, lim in (("rgb_fine", t["rgb"]), ("rgb_coarse", t["rgb"]), ("depth_fine", t["depth"]),
+                       ("rgb_instance_fine", t["inst"]), ("opacity_instance_fine", t["inst"]), ("depth_instance_fine", t["inst"])):
+            err = (got[k] - want[k]).abs()
+            # importance samples at u = 1 are a knife edge of the reference itself (test_gpu_parity.py): bound their share
+            assert (err > lim).float().mean().item() < 5e-3, (precision, k, err.max().item())
+        # PSNR delta against a 30 dB "photograph" of the reference render: what a user of the reference would measure
+        g = torch.Generator().manual_seed(0)
+        photo = (want["rgb_fine"] + torch.randn(want["rgb_fine"].shape, generator=g) * 10 ** (-30 / 20)).clamp(0, 1)
+        assert abs(helpers.psnr(got["rgb_fine"], photo) - helpers.psnr(want["rgb_fine"], photo)) < 0.05
+
+
+def test_edit_shape_render_matches_oracle_directly(scene):
+    """BASELINE configs[4] shape (test/config/edit_scannet_0113.yaml): 3 ray sets, ids [0, 4, 4], chunk 4096, on the bench
+    scene, against the oracle port of render_rays_multi (pinned to the reference by the multi_* fixtures)."""
+    from object_nerf_b200 import synthetic as S
+    from object_nerf_b200.multi_rendering import render_rays_multi
+    from oracle import onerf_oracle as O
+    sc = bench.build_scene()
+    n = 4096
+    sel = torch.linspace(0, bench.N_RAYS - 1, n).long()
+    rng = np.random.default_rng(11)
+    sets = [sc["rays"][sel].clone()]
+    for k in range(2):
+        r = sets[0].clone()
+        near = torch.from_numpy(rng.uniform(0.4, 1.2, size=n).astype(np.float32))
+        far = near + torch.from_numpy(rng.uniform(0.2, 0.9, size=n).astype(np.float32))
+        miss = torch.from_numpy(rng.random(n) < 0.3)
+        near[miss] = 0
+        far[miss] = 0
+        r[:, 6], r[:, 7] = near, far
+        sets.append(r)
+    g = sc["grid"]
+    grid = O.VoxelGrid(g["offset"], g["voxel_size"], g["shape"].tolist(), g["idx_map"], g["table"])
+    with torch.no_grad():
+        want = O.render_rays_multi(sc["weights"], grid, sc["code_table"], sets, [0, 4, 4], n_samples=64, n_importance=64)
+    lib = S.make_code_library(sc["code_table"]).to(DEV)
+    for precision, tol in (("fp32", 3e-4), ("bf16", 2e-2)):
+        got = render_rays_multi(scene["models"], scene["embeddings"], lib, [s.to(DEV) for s in sets], [0, 4, 4], N_samples=64,
+                                N_importance=64, chunk=4096, precision=precision)
+        for k in ("rgb_fine", "depth_fine", "opacity_fine", "rgb_coarse"):
+            err = (got[k].cpu() - want[k]).abs()
+            assert (err > tol).float().mean().item() < 1e-2, (precision, k, err.max().item())

@@ -458,6 +458,14 @@ def test_query_sigma_matches_oracle(precision):
     w, grid = inp["weights"]["fine"], grid_obj(inp["grid"])
     dirs = torch.zeros(xyz.shape[0], 3)
     want = O.field_eval(w, grid, xyz, dirs, code[None, :].expand(xyz.shape[0], -1))
+    if precision == "bf16":   # the mesh-extraction call pattern (tools/extract_mesh.py:83-109) routes to the same kernel
+        from object_nerf_b200 import EmbeddingVoxel
+        e_s, e_o = EmbeddingVoxel.forward(emb, xyz.to(DEV))
+        via_fwd = model.forward({"emb_xyz": e_s, "obj_voxel": e_o}, sigma_only=True)["sigma"][:, 0]
+        via_inst = model.forward_instance({"emb_xyz": e_s, "obj_voxel": e_o, "obj_code": code.to(DEV)[None].expand(xyz.shape[0], -1)},
+                                          sigma_only=True)["inst_sigma"][:, 0]
+        assert torch.equal(via_fwd, query_sigma(model, emb, xyz.to(DEV)))
+        assert torch.equal(via_inst, query_sigma(model, emb, xyz.to(DEV), obj_code=code.to(DEV)))
     got_s = query_sigma(model, emb, xyz.to(DEV), precision=precision).cpu()
     got_o = query_sigma(model, emb, xyz.to(DEV), obj_code=code.to(DEV), chunk=1024, precision=precision).cpu()
     tol = 2e-4 if precision == "fp32" else 3e-2
