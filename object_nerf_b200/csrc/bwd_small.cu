@@ -173,7 +173,8 @@ __global__ void code_scatter_kernel(const float* __restrict__ d_codes, const int
 
 }  // namespace
 
-// db of every GEMM layer, head weight / bias gradients, into the kernel-layout gradient buffer
+// head weight / bias gradients into the kernel-layout gradient buffer (the GEMM layers' bias gradients are formed by the
+// weight-gradient kernel, bwd_wgrad.cu, from the dZ tiles it streams)
 int onerf_launch_bwd_colsums(onerf_ctx* ctx, int use_voxel, int want_object, const void* ws, int64_t n_samples,
                              const float* dA_scene, const float* dA_obj, float* grad, cudaStream_t stream) {
   const GradLayout G = onerf_make_grad_layout(use_voxel);
@@ -189,9 +190,7 @@ int onerf_launch_bwd_colsums(onerf_ctx* ctx, int use_voxel, int want_object, con
   const int gemm_of[ONERF_DZ_SLOTS] = {G_S0, G_S1, G_S2, G_S3, G_S4, G_S5, G_S6, G_S7, G_SFIN, G_SDIR,
                                        G_O0, G_O1, G_O2, G_O3, G_OFIN, G_ODIR};
   int n = 0;
-  for (int d = 0; d < (want_object ? ONERF_DZ_SLOTS : 10); ++d)
-    for (int a = 0; a < T.dz_atoms[d]; ++a)
-      P.jobs[n++] = ColsumJob{T.dz_off[d] + (int64_t)a * ONERF_ATOM_BYTES, T.dz_atoms[d], 0, G.b_off[gemm_of[d]] + a * 64, 0};
+  (void)gemm_of;
   auto head = [&](int act, int weight, int64_t out, int cstride) {
     for (int a = 0; a < T.act_atoms[act]; ++a)
       P.jobs[n++] = ColsumJob{T.act_off[act] + (int64_t)a * ONERF_ATOM_BYTES, T.act_atoms[act], weight, out + a * 64, cstride};

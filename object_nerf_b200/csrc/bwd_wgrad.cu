@@ -12,7 +12,8 @@
 // live in TMEM ([128 x 256] fp32 per 128 outputs) and are flushed once with vector reductions (REDG.ADD.F32x4) into
 // the kernel-layout gradient buffer (layout.h: GradLayout).
 //   warp 4: producer (cp.async.bulk, 3-stage ring of 64-sample stages)   warp 5: tcgen05.mma issuer (owns TMEM)
-//   warps 0-3: accumulator drain
+//   warps 0-3: accumulator drain; while the ring streams they also form the bias gradients db_l = sum_s dZ_l from the
+//              dZ tiles that are passing through shared memory anyway (first column block of every layer)
 #include "common.cuh"
 #include "layout.h"
 #include "tc_common.cuh"
@@ -38,6 +39,7 @@ struct WgItem {
   int out_ld;
   int m_valid, n_valid;
   int cost;           // a_atoms + b_atoms (8 KB units per stage)
+  int64_t db_off;     // float offset of the layer's bias gradient, or -1: this item does not form it
 };
 
 struct WgParams {
@@ -104,7 +106,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
   if (threadIdx.x == 0) {
     for (int s = 0; s < WG_STAGES; ++s) {
       mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_empty + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1 + 4);   // tcgen05.commit + the four drain warps (they read the dZ tiles)
     }
     mbar_init(bar_acc_ready, 1);
     mbar_init(bar_acc_free, 4);
@@ -182,8 +184,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
       }
     }
   } else {
-    // =============================== accumulator drain ===============================
-    uint32_t ready_phase = 0;
+    // =============================== bias gradients + accumulator drain ===============================
+    uint32_t ready_phase = 0, stage = 0, phase = 0;
     int item = 0;
     int64_t item_start = 0;
     Segment seg;
@@ -191,21 +193,44 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
     const uint32_t lane_taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
     while (next_segment(P, lo, hi, item, item_start, seg)) {
       const WgItem& it = P.items[seg.item];
+      // thread t owns dZ columns 64 (t / 32) + 2 (t % 32), + 1 of the M block: word (t % 32) of every row of atom t / 32
+      const bool cs = it.db_off >= 0 && warp < it.a_atoms;
+      float c0 = 0.0f, c1 = 0.0f;
+      for (int s = seg.s0; s < seg.s1; ++s) {
+        mbar_wait(bar_full + 8 * stage, phase);
+        if (cs) {
+          const uint32_t base = sStage + stage * WG_STAGE_BYTES + (uint32_t)warp * HALF_ATOM + (uint32_t)(lane & 3) * 4u;
+#pragma unroll 8
+          for (int r = 0; r < 64; ++r) {
+            uint32_t w;
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(base + (uint32_t)r * 128u + ((((uint32_t)lane >> 2) ^ ((uint32_t)r & 7u)) << 4)));
+            c0 += __uint_as_float(w << 16);
+            c1 += __uint_as_float(w & 0xffff0000u);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_empty + 8 * stage);
+        if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (cs && warp * 64 + 2 * lane < it.m_valid) {
+        atomicAdd(P.grad + it.db_off + warp * 64 + 2 * lane, c0);
+        atomicAdd(P.grad + it.db_off + warp * 64 + 2 * lane + 1, c1);
+      }
       mbar_wait(bar_acc_ready, ready_phase);
       ready_phase ^= 1;
       tc_fence_after();
       for (int mh = 0; mh < (it.a_atoms >> 1); ++mh) {
         const int row = mh * 128 + m;
         float* out = P.grad + it.out_off + (int64_t)row * it.out_ld;
-        for (int c0 = 0; c0 < it.b_atoms * 64; c0 += 32) {
+        for (int c0_ = 0; c0_ < it.b_atoms * 64; c0_ += 32) {
           uint32_t v[32];
-          tmem_ld32(lane_taddr + (uint32_t)(mh * 256 + c0), v);
+          tmem_ld32(lane_taddr + (uint32_t)(mh * 256 + c0_), v);
           tmem_ld_wait();
           if (row < it.m_valid) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
-              if (c0 + j < it.n_valid)
-                red_add_v4(out + c0 + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+              if (c0_ + j < it.n_valid)
+                red_add_v4(out + c0_ + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
                            __uint_as_float(v[j + 3]));
           }
         }
@@ -238,6 +263,7 @@ int onerf_launch_wgrad(onerf_ctx* ctx, int use_voxel, int want_object, const voi
   const int gemm_of[ONERF_DZ_SLOTS] = {G_S0, G_S1, G_S2, G_S3, G_S4, G_S5, G_S6, G_S7, G_SFIN, G_SDIR,
                                        G_O0, G_O1, G_O2, G_O3, G_OFIN, G_ODIR};
   int n = 0;
+  bool db_done[ONERF_DZ_SLOTS] = {};
   // input blocks of a layer: (activation slot, first atom, atoms, first kernel-K column, valid columns)
   auto add = [&](int dz, int act, int b_atom0, int b_atoms, int col0, int n_valid) {
     const int g = gemm_of[dz];
@@ -250,6 +276,8 @@ int onerf_launch_wgrad(onerf_ctx* ctx, int use_voxel, int want_object, const voi
     it.out_off = G.w_off[g] + col0; it.out_ld = L.g[g].K;
     it.m_valid = out_n; it.n_valid = n_valid;
     it.cost = it.a_atoms + it.b_atoms;
+    it.db_off = db_done[dz] ? -1 : G.b_off[g];   // the first column block of a layer also forms its bias gradient
+    db_done[dz] = true;
   };
   const int xa = use_voxel ? 4 : 1;             // leading X atoms (256 / 64 columns)
   auto x_blocks = [&](int dz, int kx) {         // X[0, kx)
