@@ -202,7 +202,9 @@ int onerf_launch_bwd_colsums(onerf_ctx* ctx, int use_voxel, int want_object, con
     head(16, 4, G.orgb_w, 64);
   }
   P.n_jobs = n;
-  int gx = T.n_tiles < 16 ? T.n_tiles : 16;
+  int gx = (8 * ctx->num_sms + n - 1) / n;     // ~8 CTAs per SM in flight: the kernel is a pure HBM stream
+  if (gx > T.n_tiles) gx = T.n_tiles;
+  if (gx < 1) gx = 1;
   atom_colsum_kernel<<<dim3(gx, n), 256, 0, stream>>>(P);
   ONERF_LAUNCH_CHECK(ctx);
   int blocks = (int)((n_samples + 255) / 256 < 4 * ctx->num_sms ? (n_samples + 255) / 256 : 4 * ctx->num_sms);
