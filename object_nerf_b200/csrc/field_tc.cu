@@ -30,6 +30,7 @@
 #include "encode.cuh"
 #include "field_common.cuh"
 #include "tc_chain.cuh"
+#include "field_pe.cuh"
 
 // In-kernel clock64() timeline (tools/timeline.py): compiled in only with -DONERF_TIMELINE (make TIMELINE=1).
 #ifdef ONERF_TIMELINE
@@ -79,73 +80,6 @@ __device__ __forceinline__ void dump_packed(const DumpDst& d, int n, int word, c
     for (int j = 0; j < NP; ++j) m |= (((~pk[j]) >> 15) & 1u) << (2 * j) | ((~pk[j]) >> 31) << (2 * j + 1);
     d.mask[word * 128] = m;
   }
-}
-
-// 16-byte chunk `chunk` (8 bf16 of K) of row `row` in an A buffer made of SWIZZLE_128B atoms (64 K per atom)
-__device__ __forceinline__ uint32_t a_chunk_addr(uint32_t base, int row, int chunk) {
-  return base + (uint32_t)(chunk >> 3) * ATOM_BYTES + (uint32_t)row * 128u + (uint32_t)(((chunk & 7) ^ (row & 7)) << 4);
-}
-__device__ __forceinline__ void st_chunk(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-
-// PE of 8 channels -> 13 chunks [f | sin 2^k f | cos 2^k f]_k at chunk0 + stride * block
-__device__ __forceinline__ void pe8_to_chunks(uint32_t xbase, int row, int chunk0, int stride, const float* f) {
-  float s[8], c[8];
-  st_chunk(a_chunk_addr(xbase, row, chunk0), pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]),
-           pack_bf16(f[6], f[7]));
-#pragma unroll
-  for (int j = 0; j < 8; ++j) __sincosf(f[j], &s[j], &c[j]);  // |f| = O(1), 6 octaves: error stays << bf16 ulp
-#pragma unroll
-  for (int k = 0; k < 6; ++k) {
-    st_chunk(a_chunk_addr(xbase, row, chunk0 + stride * (1 + 2 * k)), pack_bf16(s[0], s[1]), pack_bf16(s[2], s[3]),
-             pack_bf16(s[4], s[5]), pack_bf16(s[6], s[7]));
-    st_chunk(a_chunk_addr(xbase, row, chunk0 + stride * (2 + 2 * k)), pack_bf16(c[0], c[1]), pack_bf16(c[2], c[3]),
-             pack_bf16(c[4], c[5]), pack_bf16(c[6], c[7]));
-    if (k < 5) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {  // double-angle step to the next octave
-        const float s2 = 2.0f * s[j] * c[j];
-        c[j] = fmaf(-2.0f * s[j], s[j], 1.0f);
-        s[j] = s2;
-      }
-    }
-  }
-}
-
-// PE10(xyz): 63 values in reference order + one zero -> 8 chunks starting at chunk0.  Values are packed to
-// bf16 pairs as they are produced (the stream position is a compile-time constant after unrolling).
-__device__ __forceinline__ void pe_xyz_to_chunks(uint32_t xbase, int row, int chunk0, float x, float y, float z) {
-  uint32_t pk[32];
-  float pend = 0.0f;
-  int pos = 0;
-  auto emit = [&](float val) {
-    if ((pos & 1) == 0) pend = val;
-    else pk[pos >> 1] = pack_bf16(pend, val);
-    ++pos;
-  };
-  emit(x); emit(y); emit(z);
-  float s[3], c[3];
-  sincosf(x, &s[0], &c[0]);
-  sincosf(y, &s[1], &c[1]);
-  sincosf(z, &s[2], &c[2]);
-#pragma unroll
-  for (int k = 0; k < 10; ++k) {
-    emit(s[0]); emit(s[1]); emit(s[2]);
-    emit(c[0]); emit(c[1]); emit(c[2]);
-    if (k < 9) {
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {  // double-angle step to the next octave
-        const float s2 = 2.0f * s[j] * c[j];
-        c[j] = fmaf(-2.0f * s[j], s[j], 1.0f);
-        s[j] = s2;
-      }
-    }
-  }
-  emit(0.0f);
-#pragma unroll
-  for (int q = 0; q < 8; ++q)
-    st_chunk(a_chunk_addr(xbase, row, chunk0 + q), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -455,8 +389,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_tc_kernel(const __grid_c
 static long long* g_timeline = nullptr;
 extern "C" void onerf_debug_timeline(void* dev_buf) { g_timeline = reinterpret_cast<long long*>(dev_buf); }
 
+int onerf_launch_field_bf16_two_tile(onerf_ctx* ctx, const FieldParams& fp, cudaStream_t stream);   // field_tc2.cu
+
 int onerf_launch_field_bf16(onerf_ctx* ctx, const FieldParams& fp, cudaStream_t stream) {
   const PackLayout& L = fp.L;
+  // The voxel model's inference forward runs on the two-tile kernel (field_tc2.cu).  This one-tile kernel serves the
+  // plain-PE model and the training forward (activation dump); ONERF_TC_ONE_TILE=1 forces it everywhere (A/B runs).
+  static const int one_tile = [] { const char* v = getenv("ONERF_TC_ONE_TILE"); return (v && v[0] == '1') ? 1 : 0; }();
+  if (L.use_voxel && !fp.train_ws && !one_tile) return onerf_launch_field_bf16_two_tile(ctx, fp, stream);
   TcParams P;
   memset(&P, 0, sizeof(P));
   P.f = fp;

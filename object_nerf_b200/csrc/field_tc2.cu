@@ -1,0 +1,598 @@
+// Two-tile tcgen05 implementation of the fused encode + two-branch MLP for sm_100a (voxel model, inference).
+//
+// The one-tile kernel (field_tc.cu) leaves the tensor pipe idle two thirds of the time: one 128-row tile has a single
+// dependency chain  MMA(layer l) -> epilogue(l) -> MMA(l + 1)  and the ~950-cycle epilogues of its 16 warps cannot hide
+// behind its own MMAs (profiles/r01_experiments.md).  Here a CTA owns TWO 128-row tiles (A, B) that walk the layer
+// program in lockstep, half a layer apart: while the 16 epilogue warps drain a layer half of one tile, the tensor pipe
+// runs the same layer half of the other.
+//   slot order per two-half layer l :  (A,l,h0) (B,l,h0) (A,l,h1) (B,l,h1)      [X-fed: (A,h0) (A,h1) (B,h0) (B,h1)]
+//   TMEM (512 columns)              :  tile t: accumulator [256 t, +128), activations [256 t + 128, +128) IN PLACE
+//                                      (bf16 pairs): the outputs of half 0 wait in 16 registers per thread until the
+//                                      MMAs of half 1 have read the old activations
+//   shared memory                   :  ONE 96 KB buffer XS for the encoded input X (the A operand of the four X-fed layers),
+//                                      regenerated from 27 raw features per sample (24 trilinear voxel channels + xyz,
+//                                      kept in shared memory for both tiles) by four dedicated encode warps each time a
+//                                      tile reaches an X-fed layer; 3 x 24 KB weight ring; biases
+//   warps 0-15  epilogue (both tiles, alternating)    warp 16  weight producer (cp.async.bulk)
+//   warp 17     tcgen05.mma issuer (owns TMEM)        warps 20-23  encode: trilinear gather of the NEXT tile pair,
+//   (warps 18-19 idle: they complete the control warpgroup)        positional encoding into XS
+// Registers are re-divided between the warpgroups with setmaxnreg (epilogue 104: two 16-register stashes; control 40;
+// encode 56).
+// mbarriers: full / empty (ring), acc_ready[t] (MMA -> epilogue), acc_free[t] (epilogue has loaded the accumulator: the
+// tile's next MMAs may overwrite it), h_ready[t] (a layer's activations are written), xs_ready / xs_free (XS hand-over).
+// Arithmetic is that of the one-tile kernel (same K order, same epilogue math): results are bit-identical to it.
+//
+// Reference semantics: models/rendering.py:85-137, models/nerf_model.py:97-152,
+// models/embedding_helper.py:325-411, render_tools/multi_rendering.py:16-93.
+#include <cuda_bf16.h>
+#include <cstdlib>
+
+#include "encode.cuh"
+#include "field_common.cuh"
+#include "field_pe.cuh"
+
+namespace {
+
+using namespace tc;
+
+constexpr int T2_NSTAGE = 3;
+constexpr int T2_SLAB_BYTES = 8192;          // 128 rows x 64 B: one K-slab (32 of K) of one N = 128 half
+constexpr int T2_STAGE_SLABS = 3;
+constexpr int T2_STAGE_BYTES = T2_STAGE_SLABS * T2_SLAB_BYTES;   // 24 KB
+constexpr int T2_MAX_GROUPS = 8;
+constexpr int T2_MAX_LAYERS = 16;
+constexpr int T2_MAX_SLOTS = 56;
+constexpr int T2_MAX_XUSE = 4;
+constexpr int T2_EPI_THREADS = 512;
+// warpgroups (setmaxnreg works per group of 4 warps): 0-3 epilogue, 4 = {producer, MMA, 2 idle}, 5 = encode
+constexpr int T2_PRODUCER_WARP = 16, T2_MMA_WARP = 17, T2_ENC_WARP0 = 20, T2_ENC_WARPS = 4;
+constexpr int T2_THREADS = 32 * (T2_ENC_WARP0 + T2_ENC_WARPS);   // 768: 80 registers per thread at launch
+constexpr int T2_REGS_EPI = 104, T2_REGS_CTRL = 40, T2_REGS_ENC = 56;   // 512 x 104 + 128 x 40 + 128 x 56 = 65 536
+constexpr int T2_NF = 27;                     // raw features per sample: 24 trilinear channels, x, y, z
+constexpr float kLeaky = 0.01f;
+
+enum Epi { EPI_HIDDEN = 0, EPI_HIDDEN_RC = 1, EPI_HIDDEN_SIGMA = 2, EPI_FINAL = 3, EPI_DIR = 4 };
+enum SlotFlags { SLOT_WAIT_H = 1, SLOT_WAIT_XS = 2, SLOT_XS_RELEASE = 4 };
+
+struct T2Layer {
+  int N;            // outputs of the layer
+  int nhalf;        // 2: computed as two N = 128 halves; 1: N <= 128
+  int nslab_x, nslab_h;
+  int epi, branch, rc_base;
+  int writes_h;     // the epilogue leaves activations for the next layer (everything except the dir layers)
+  int64_t img_off, bias_off;
+  int ngroups, n_xgroups;
+  int groups[T2_MAX_GROUPS];   // bits [0,5) first slab (inside X or H), [5,8) slab count (1..3), bit 8: from H
+};
+struct T2Slot {
+  uint8_t tile, layer, half, flags;
+};
+struct T2Params {
+  FieldParams f;
+  T2Layer layers[T2_MAX_LAYERS];
+  int n_layers;
+  T2Slot slots[T2_MAX_SLOTS];
+  int n_slots;
+  int n_xuse;                       // X-fed layers per tile, in program order
+  int xuse_full[T2_MAX_XUSE];       // 1: the layer reads all 384 columns (object branch), 0: the first 288 (scene)
+};
+
+// ------------------------------------------------------------------------------------------------
+// epilogue math (same operations as field_tc.cu)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t leaky_bf16x2(uint32_t x) {
+  __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&x);
+  const __nv_bfloat162 slope = __floats2bfloat162_rn(kLeaky, kLeaky);
+  v = __hmax2(v, __hmul2(v, slope));
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// acc + bias -> bf16 (-> LeakyReLU on packed pairs): NC columns -> NC / 2 packed words
+template <int NC, bool ACT, bool BIAS_GLOBAL>
+__device__ __forceinline__ void math_hidden(const uint32_t* v, const float* bias, uint32_t* pk) {
+#pragma unroll
+  for (int j4 = 0; j4 < NC / 4; ++j4) {
+    float4 b;
+    if (BIAS_GLOBAL) b = __ldg(reinterpret_cast<const float4*>(bias) + j4);
+    else b = *(reinterpret_cast<const float4*>(bias) + j4);
+    uint32_t p0 = pack_bf16(__uint_as_float(v[4 * j4 + 0]) + b.x, __uint_as_float(v[4 * j4 + 1]) + b.y);
+    uint32_t p1 = pack_bf16(__uint_as_float(v[4 * j4 + 2]) + b.z, __uint_as_float(v[4 * j4 + 3]) + b.w);
+    if (ACT) { p0 = leaky_bf16x2(p0); p1 = leaky_bf16x2(p1); }
+    pk[2 * j4] = p0;
+    pk[2 * j4 + 1] = p1;
+  }
+}
+// last hidden layer of a branch: plus the sigma head as an fp32 dot product on the un-rounded activations
+template <int NC>
+__device__ __forceinline__ float math_hidden_sigma(const uint32_t* v, const float* bias, const float* headw, uint32_t* pk) {
+  float part = 0.0f;
+#pragma unroll
+  for (int j4 = 0; j4 < NC / 4; ++j4) {
+    const float4 b = *(reinterpret_cast<const float4*>(bias) + j4);
+    const float4 w = __ldg(reinterpret_cast<const float4*>(headw) + j4);
+    float t0 = __uint_as_float(v[4 * j4 + 0]) + b.x, t1 = __uint_as_float(v[4 * j4 + 1]) + b.y;
+    float t2 = __uint_as_float(v[4 * j4 + 2]) + b.z, t3 = __uint_as_float(v[4 * j4 + 3]) + b.w;
+    t0 = fmaxf(t0, t0 * kLeaky); t1 = fmaxf(t1, t1 * kLeaky); t2 = fmaxf(t2, t2 * kLeaky); t3 = fmaxf(t3, t3 * kLeaky);
+    part = fmaf(t0, w.x, part); part = fmaf(t1, w.y, part); part = fmaf(t2, w.z, part); part = fmaf(t3, w.w, part);
+    pk[2 * j4] = pack_bf16(t0, t1);
+    pk[2 * j4 + 1] = pack_bf16(t2, t3);
+  }
+  return part;
+}
+// direction layer: LeakyReLU(acc + per-ray constant) feeds the 3-wide rgb head directly (fp32 dots)
+template <int NC>
+__device__ __forceinline__ void math_dir(const uint32_t* v, const float* rcbias, const float* headw, int head_ld, float& p0,
+                                         float& p1, float& p2) {
+#pragma unroll
+  for (int j4 = 0; j4 < NC / 4; ++j4) {
+    const float4 b = __ldg(reinterpret_cast<const float4*>(rcbias) + j4);
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(headw) + j4);
+    const float4 w1 = __ldg(reinterpret_cast<const float4*>(headw + head_ld) + j4);
+    const float4 w2 = __ldg(reinterpret_cast<const float4*>(headw + 2 * head_ld) + j4);
+    float t0 = __uint_as_float(v[4 * j4 + 0]) + b.x, t1 = __uint_as_float(v[4 * j4 + 1]) + b.y;
+    float t2 = __uint_as_float(v[4 * j4 + 2]) + b.z, t3 = __uint_as_float(v[4 * j4 + 3]) + b.w;
+    t0 = fmaxf(t0, t0 * kLeaky); t1 = fmaxf(t1, t1 * kLeaky); t2 = fmaxf(t2, t2 * kLeaky); t3 = fmaxf(t3, t3 * kLeaky);
+    p0 = fmaf(t0, w0.x, p0); p0 = fmaf(t1, w0.y, p0); p0 = fmaf(t2, w0.z, p0); p0 = fmaf(t3, w0.w, p0);
+    p1 = fmaf(t0, w1.x, p1); p1 = fmaf(t1, w1.y, p1); p1 = fmaf(t2, w1.z, p1); p1 = fmaf(t3, w1.w, p1);
+    p2 = fmaf(t0, w2.x, p2); p2 = fmaf(t1, w2.y, p2); p2 = fmaf(t2, w2.z, p2); p2 = fmaf(t3, w2.w, p2);
+  }
+}
+
+// shared-memory carve-up (byte offsets from the 1024-byte aligned base)
+constexpr uint32_t OFF_X = 0;
+constexpr uint32_t OFF_B = OFF_X + 6 * ATOM_BYTES;                    // weight ring
+constexpr uint32_t OFF_F = OFF_B + T2_NSTAGE * T2_STAGE_BYTES;        // [2][27][128] floats: raw features of both tiles
+constexpr uint32_t OFF_MUTE = OFF_F + 2 * T2_NF * 128 * 4;            // [2 parities][2 tiles][128] bytes
+constexpr uint32_t OFF_BIAS = OFF_MUTE + 512;                         // [MAX_LAYERS][256] floats
+constexpr uint32_t OFF_SCRATCH = OFF_BIAS + T2_MAX_LAYERS * 256 * 4;  // [128][4][4] floats
+constexpr uint32_t OFF_BAR = OFF_SCRATCH + TM * 4 * 4 * 4;
+constexpr uint32_t T2_SMEM_BYTES = OFF_BAR + 256 + 1024;
+
+struct EpiShared {   // what the epilogue code needs besides the per-event arguments
+  const T2Params* P;
+  uint8_t* smem;             // generic pointer to the aligned shared-memory base
+  uint32_t sbase;            // its shared-window address
+  uint32_t lane_taddr;       // TMEM address of this warp's lane quarter, column 0
+  int row, cq, lane;
+};
+struct TileMeta {            // per tile of the current pair
+  int ray, si;
+  bool live;
+};
+
+// One epilogue event: layer `l`, half `h` of tile T.  `stash`: the packed outputs of half 0 of a two-half layer.
+template <int T>
+__device__ __forceinline__ void epi_event(const EpiShared& S, int l, int h, const TileMeta& M, int parity, uint32_t (&stash)[16],
+                                          uint32_t& acc_phase, float& sigma_part) {
+  const T2Params& P = *S.P;
+  const T2Layer& Ly = P.layers[l];
+  const FieldParams& p = P.f;
+  const float* Pf = reinterpret_cast<const float*>(p.packed);
+  const float* bias_tab = reinterpret_cast<const float*>(S.smem + OFF_BIAS);
+  float* scratch = reinterpret_cast<float*>(S.smem + OFF_SCRATCH);
+  const uint32_t bar_acc_ready = S.sbase + OFF_BAR + 16 * T2_NSTAGE, bar_acc_free = bar_acc_ready + 16, bar_h_ready = bar_acc_free + 16;
+  const int HW = Ly.N >> (Ly.nhalf - 1);       // 128, or 64 for the object dir layer
+  const int n = h * HW + S.cq * (HW >> 2);     // first output column of this thread
+  const uint32_t acc_addr = S.lane_taddr + (uint32_t)(T * 256 + S.cq * (HW >> 2));
+  const uint32_t h_addr = S.lane_taddr + (uint32_t)(T * 256 + 128);
+  const float* rc = p.ray_const + (int64_t)M.ray * ONERF_RAY_CONST_FLOATS;
+  mbar_wait(bar_acc_ready + 8 * T, acc_phase);
+  acc_phase ^= 1;
+  tc_fence_after();
+  uint32_t v[32];
+  if (HW == 128) { tmem_ld16(acc_addr, v); tmem_ld16(acc_addr + 16, v + 16); }
+  else tmem_ld16(acc_addr, v);
+  tmem_ld_wait();
+  // the accumulator is in registers: the tile's next MMAs may overwrite it
+  tc_fence_before();
+  __syncwarp();
+  if (S.lane == 0) mbar_arrive(bar_acc_free + 8 * T);
+  uint32_t pk[16];
+  const float* bias = bias_tab + l * 256 + n;
+  if (Ly.epi == EPI_DIR) {
+    const float* headw = Pf + (Ly.branch ? p.L.orgb_w : p.L.rgb_w) + n;
+    float part0 = 0.0f, part1 = 0.0f, part2 = 0.0f;
+    if (HW == 128) math_dir<32>(v, rc + Ly.rc_base + n, headw, Ly.N, part0, part1, part2);
+    else math_dir<16>(v, rc + Ly.rc_base + n, headw, Ly.N, part0, part1, part2);
+    // combine the four column quarters of this row through shared memory, finish the heads, write out
+    float* sc = scratch + (S.row * 4 + S.cq) * 4;
+    sc[0] = sigma_part; sc[1] = part0; sc[2] = part1; sc[3] = part2;
+    asm volatile("bar.sync 1, %0;" ::"n"(T2_EPI_THREADS) : "memory");
+    if (S.cq == 0 && M.live) {
+      const float4 a1 = *reinterpret_cast<const float4*>(scratch + (S.row * 4 + 1) * 4);
+      const float4 a2 = *reinterpret_cast<const float4*>(scratch + (S.row * 4 + 2) * 4);
+      const float4 a3 = *reinterpret_cast<const float4*>(scratch + (S.row * 4 + 3) * 4);
+      const float* hb = Pf + (Ly.branch ? p.L.orgb_b : p.L.rgb_b);
+      float sg = sigma_part + a1.x + a2.x + a3.x + __ldg(Pf + (Ly.branch ? p.L.osigma_b : p.L.sigma_b));
+      const float r = 1.0f / (1.0f + __expf(-(part0 + a1.y + a2.y + a3.y + __ldg(hb + 0))));
+      const float gch = 1.0f / (1.0f + __expf(-(part1 + a1.z + a2.z + a3.z + __ldg(hb + 1))));
+      const float b = 1.0f / (1.0f + __expf(-(part2 + a1.w + a2.w + a3.w + __ldg(hb + 2))));
+      const int mute = S.smem[OFF_MUTE + (parity * 2 + T) * 128 + S.row];
+      if (mute & (Ly.branch ? 2 : 1)) sg = -1e5f;
+      float* outp = Ly.branch ? p.obj_out : p.scene_out;
+      reinterpret_cast<float4*>(outp)[(int64_t)M.ray * p.out_stride + M.si] = make_float4(r, gch, b, sg);
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(T2_EPI_THREADS) : "memory");  // scratch reusable
+    return;
+  }
+  switch (Ly.epi) {
+    case EPI_HIDDEN: math_hidden<32, true, false>(v, bias, pk); break;
+    case EPI_HIDDEN_RC: math_hidden<32, true, true>(v, rc + Ly.rc_base + n, pk); break;
+    case EPI_FINAL: math_hidden<32, false, false>(v, bias, pk); break;
+    default: {   // EPI_HIDDEN_SIGMA
+      const float* headw = Pf + (Ly.branch ? p.L.osigma_w : p.L.sigma_w) + n;
+      const float part = math_hidden_sigma<32>(v, bias, headw, pk);
+      sigma_part = (h == 0) ? part : sigma_part + part;
+    } break;
+  }
+  if (Ly.nhalf == 2 && h == 0) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) stash[j] = pk[j];
+    return;
+  }
+  // all MMAs of this layer have completed (this half's accumulator was ready): overwrite the activations in place
+  if (Ly.nhalf == 2) {
+    tmem_st16(h_addr + (uint32_t)(S.cq * 16), stash);
+    tmem_st16(h_addr + (uint32_t)(64 + S.cq * 16), pk);
+  } else {
+    tmem_st16(h_addr + (uint32_t)(S.cq * 16), pk);
+  }
+  tmem_st_wait();
+  tc_fence_before();
+  __syncwarp();
+  if (S.lane == 0) mbar_arrive(bar_h_ready + 8 * T);
+}
+
+__global__ void __launch_bounds__(T2_THREADS, 1) field_tc2_kernel(const __grid_constant__ T2Params P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const FieldParams& p = P.f;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // ---- shared memory carve-up (base is 1024-byte aligned: required by the 128B swizzle) ----
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sX = sbase + OFF_X, sB = sbase + OFF_B, sBar = sbase + OFF_BAR;
+  const uint32_t bar_full = sBar, bar_empty = sBar + 8 * T2_NSTAGE;
+  const uint32_t bar_acc_ready = sBar + 16 * T2_NSTAGE;              // [2]
+  const uint32_t bar_acc_free = bar_acc_ready + 16;                  // [2]
+  const uint32_t bar_h_ready = bar_acc_free + 16;                    // [2]
+  const uint32_t bar_xs_ready = bar_h_ready + 16, bar_xs_free = bar_xs_ready + 8;
+  const uint32_t tmem_slot = bar_xs_free + 8;
+  uint8_t* gen_base = smem_raw + (sbase - smem_u32(smem_raw));
+  float* feat = reinterpret_cast<float*>(gen_base + OFF_F);
+  uint8_t* mute_tab = gen_base + OFF_MUTE;
+  float* bias_tab = reinterpret_cast<float*>(gen_base + OFF_BIAS);
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - sbase));
+  const float* Pf = reinterpret_cast<const float*>(p.packed);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < T2_NSTAGE; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(bar_acc_ready + 8 * t, 1);
+      mbar_init(bar_acc_free + 8 * t, T2_EPI_THREADS / 32);
+      mbar_init(bar_h_ready + 8 * t, T2_EPI_THREADS / 32);
+    }
+    mbar_init(bar_xs_ready, T2_ENC_WARPS);
+    mbar_init(bar_xs_free, 1);
+    fence_barrier_init();
+  }
+  if (warp == T2_MMA_WARP) tmem_alloc(tmem_slot, 512);
+  for (int i = threadIdx.x; i < P.n_layers * 256; i += T2_THREADS) {
+    const int l = i >> 8, c = i & 255;
+    bias_tab[i] = (c < P.layers[l].N) ? __ldg(Pf + P.layers[l].bias_off + c) : 0.0f;
+  }
+  // XS starts as zeros: columns a layer's weights do not reach (scene layers: 272..287, pads) must stay finite
+  for (uint32_t i = threadIdx.x; i < 6u * ATOM_BYTES / 16u; i += T2_THREADS)
+    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(sX + i * 16u), "r"(0u) : "memory");
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  const int64_t total = (int64_t)p.n_rays * p.S;
+  const int64_t n_tiles = (total + TM - 1) / TM;
+  const int64_t n_pairs = (n_tiles + 1) / 2;
+  const uint8_t* blob = reinterpret_cast<const uint8_t*>(p.packed);
+
+  if (warp >= 16 && warp < T2_ENC_WARP0) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(T2_REGS_CTRL));
+  else if (warp >= T2_ENC_WARP0) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(T2_REGS_ENC));
+  else asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(T2_REGS_EPI));
+
+  if (warp == T2_PRODUCER_WARP) {
+    // =============================== weight producer ===============================
+    uint32_t stage = 0, phase = 0;
+    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+      for (int si = 0; si < P.n_slots; ++si) {
+        const T2Slot sl = P.slots[si];
+        const T2Layer& Ly = P.layers[sl.layer];
+        const uint32_t slab_bytes = (uint32_t)Ly.N * 64u, half_bytes = slab_bytes >> (Ly.nhalf - 1);
+        const uint8_t* src = blob + Ly.img_off + (size_t)sl.half * half_bytes;
+        for (int gi = 0; gi < Ly.ngroups; ++gi) {
+          const int grp = Ly.groups[gi];
+          const int first = grp & 31, cnt = (grp >> 5) & 7;
+          const int gslab = ((grp >> 8) & 1) ? Ly.nslab_x + first : first;
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx(bar_full + 8 * stage, (uint32_t)cnt * half_bytes);
+            for (int i2 = 0; i2 < cnt; ++i2)
+              tma_bulk_g2s(sB + stage * T2_STAGE_BYTES + (uint32_t)i2 * half_bytes, src + (size_t)(gslab + i2) * slab_bytes,
+                           half_bytes, bar_full + 8 * stage);
+          }
+          __syncwarp();
+          if (++stage == T2_NSTAGE) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == T2_MMA_WARP) {
+    // =============================== MMA issuer ===============================
+    uint32_t stage = 0, phase = 0, xs_phase = 0;
+    uint32_t free_bits = 0, h_bits = 0;   // per-tile barrier phases, bit t
+    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+      for (int si = 0; si < P.n_slots; ++si) {
+        const T2Slot sl = P.slots[si];
+        const T2Layer& Ly = P.layers[sl.layer];
+        const int t = sl.tile;
+        const uint32_t idesc = make_idesc(Ly.N >> (Ly.nhalf - 1));
+        const uint32_t half_bytes = ((uint32_t)Ly.N * 64u) >> (Ly.nhalf - 1);
+        const uint32_t hb16 = half_bytes >> 4;
+        const uint32_t d_tmem = tmem_base + (uint32_t)(t * 256);
+        const uint32_t h_tmem = tmem_base + (uint32_t)(t * 256 + 128);
+        // the epilogue of the tile's previous slot holds the accumulator in registers
+        mbar_wait(bar_acc_free + 8 * t, (free_bits >> t) & 1u);
+        free_bits ^= 1u << t;
+        if (sl.flags & SLOT_WAIT_H) {   // the previous layer's activations are written
+          mbar_wait(bar_h_ready + 8 * t, (h_bits >> t) & 1u);
+          h_bits ^= 1u << t;
+        }
+        tc_fence_after();
+        for (int gi = 0; gi < Ly.ngroups; ++gi) {
+          const int grp = Ly.groups[gi];
+          const int first = grp & 31, cnt = (grp >> 5) & 7;
+          const bool from_h = (grp >> 8) & 1;
+          const uint32_t b_lo0 = (((sB + stage * T2_STAGE_BYTES) >> 4) & 0x3FFFu) | 0x10000u;
+          const uint32_t accum0 = (gi > 0) ? 1u : 0u;
+          if (gi == 0 && (sl.flags & SLOT_WAIT_XS)) {   // XS holds this tile's X
+            mbar_wait(bar_xs_ready, xs_phase);
+            xs_phase ^= 1;
+          }
+          mbar_wait(bar_full + 8 * stage, phase);
+          tc_fence_after();
+          if (elect_one()) {
+            uint32_t accum = accum0;
+            if (!from_h) {
+#pragma unroll
+              for (int i2 = 0; i2 < T2_STAGE_SLABS; ++i2) {
+                if (i2 < cnt) {
+                  const int s = first + i2;     // X slab: atom s / 2, 64-byte half s % 2
+                  const uint32_t a_lo = ((((sX + (uint32_t)(s >> 1) * ATOM_BYTES) >> 4) & 0x3FFFu) | 0x10000u) + (uint32_t)(s & 1) * 4u;
+                  const uint32_t b_lo = b_lo0 + (uint32_t)i2 * hb16;
+                  umma_bf16(d_tmem, make_desc_hl(a_lo, DESC_HI_SW128), make_desc_hl(b_lo, DESC_HI_SW64), idesc, accum);
+                  umma_bf16(d_tmem, make_desc_hl(a_lo + 2u, DESC_HI_SW128), make_desc_hl(b_lo + 2u, DESC_HI_SW64), idesc, 1u);
+                  accum = 1u;
+                }
+              }
+            } else {
+#pragma unroll
+              for (int i2 = 0; i2 < T2_STAGE_SLABS; ++i2) {
+                if (i2 < cnt) {
+                  const uint32_t b_lo = b_lo0 + (uint32_t)i2 * hb16;
+                  const uint32_t a0 = h_tmem + (uint32_t)(first + i2) * 16u;
+                  umma_bf16_ts(d_tmem, a0, make_desc_hl(b_lo, DESC_HI_SW64), idesc, accum);
+                  umma_bf16_ts(d_tmem, a0 + 8u, make_desc_hl(b_lo + 2u, DESC_HI_SW64), idesc, 1u);
+                  accum = 1u;
+                }
+              }
+            }
+            umma_commit(bar_empty + 8 * stage);
+            if (gi == Ly.n_xgroups - 1 && (sl.flags & SLOT_XS_RELEASE)) umma_commit(bar_xs_free);
+            if (gi == Ly.ngroups - 1) umma_commit(bar_acc_ready + 8 * t);
+          }
+          __syncwarp();
+          if (++stage == T2_NSTAGE) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= T2_ENC_WARP0) {
+    // =============================== encode warps: raw features and XS ===============================
+    const int row = (warp - T2_ENC_WARP0) * 32 + lane;
+    const GridView g = load_grid_view(p.grid);
+    // trilinear gather of one tile's 27 raw features per row + the mute flags of the row
+    auto gather = [&](int t, int64_t tile, int parity) {
+      const int64_t e = tile * TM + row;
+      const bool live = e < total;
+      const int ray = live ? (int)(e / p.S) : 0;
+      const int si = live ? (int)(e - (int64_t)ray * p.S) : 0;
+      const float* rr = p.rays + (int64_t)ray * 8;
+      const float zz = live ? __ldg(p.z + (int64_t)ray * p.z_stride + si) : 0.0f;
+      float x = fmaf(__ldg(rr + 3), zz, __ldg(rr + 0));
+      float y = fmaf(__ldg(rr + 4), zz, __ldg(rr + 1));
+      float z = fmaf(__ldg(rr + 5), zz, __ldg(rr + 2));
+      if (p.xyz && live) {
+        const float* qq = p.xyz + ((int64_t)ray * p.S + si) * 3;
+        x = __ldg(qq); y = __ldg(qq + 1); z = __ldg(qq + 2);
+      }
+      if (!live) { x = 0.f; y = 0.f; z = 0.f; }
+      int mute = 0;  // bit 0: scene sigma muted, bit 1: object sigma muted
+      if (live && p.mute_zero_rays && __ldg(p.z + (int64_t)ray * p.z_stride + (p.S - 1)) == 0.0f) mute = 3;
+      if (live && mute == 0 && p.n_boxes > 0 && point_in_boxes(p.boxes, p.n_boxes, x, y, z)) mute = 1;
+      mute_tab[(parity * 2 + t) * 128 + row] = (uint8_t)mute;
+      float* F = feat + (size_t)t * T2_NF * 128 + row;
+      float f[8];
+      voxel_trilinear<0, 8, false>(g, x, y, z, f);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) F[c * 128] = f[c];
+      voxel_trilinear<8, 8, false>(g, x, y, z, f);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) F[(8 + c) * 128] = f[c];
+      voxel_trilinear<16, 8, false>(g, x, y, z, f);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) F[(16 + c) * 128] = f[c];
+      F[24 * 128] = x; F[25 * 128] = y; F[26 * 128] = z;
+    };
+    uint32_t regen = 0;   // regenerations of XS so far (the r-th one waits for the release of the (r-1)-th)
+    bool first_pair = true;
+    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+      const int parity = (int)(((pair - blockIdx.x) / gridDim.x) & 1);
+      if (first_pair) {
+        gather(0, 2 * pair, parity);
+        gather(1, 2 * pair + 1, parity);
+        first_pair = false;
+      }
+      for (int u = 0; u < P.n_xuse; ++u) {
+        for (int t = 0; t < 2; ++t) {
+          if (regen > 0) mbar_wait(bar_xs_free, (regen - 1) & 1);   // every MMA that read the previous X has completed
+          const float* F = feat + (size_t)t * T2_NF * 128 + row;
+          float f[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) f[c] = F[c * 128];
+          pe8_to_chunks(sX, row, 0, 2, f);          // scene channels 0-7 : chunks 0, 2, 4, ...
+#pragma unroll
+          for (int c = 0; c < 8; ++c) f[c] = F[(8 + c) * 128];
+          pe8_to_chunks(sX, row, 1, 2, f);          // scene channels 8-15: chunks 1, 3, 5, ...
+          pe_xyz_to_chunks(sX, row, 26, F[24 * 128], F[25 * 128], F[26 * 128]);   // columns 208..271
+          if (P.xuse_full[u]) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) f[c] = F[(16 + c) * 128];
+            pe8_to_chunks(sX, row, 34, 1, f);       // object voxel block starts at column 272 = chunk 34
+            st_chunk(a_chunk_addr(sX, row, 47), 0u, 0u, 0u, 0u);  // columns 376..383
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_xs_ready);
+          ++regen;
+          if (u == P.n_xuse - 1) {   // this tile's features are no longer needed: fetch the next pair's
+            const int64_t next = pair + gridDim.x;
+            if (next < n_pairs) gather(t, 2 * next + t, parity ^ 1);
+          }
+        }
+      }
+    }
+  } else if (warp < 16) {
+    // =============================== epilogue warps ===============================
+    EpiShared S;
+    S.P = &P; S.smem = gen_base; S.sbase = sbase;
+    const int q = warp & 3;
+    S.cq = warp >> 2; S.lane = lane; S.row = q * 32 + lane;
+    S.lane_taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint32_t acc_phase[2] = {0, 0};
+    uint32_t stash0[16], stash1[16];
+    float sigma_part[2] = {0.0f, 0.0f};
+    // nothing holds the accumulators before the very first slots
+    if (lane == 0) {
+      mbar_arrive(bar_acc_free);
+      mbar_arrive(bar_acc_free + 8);
+    }
+    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+      const int parity = (int)(((pair - blockIdx.x) / gridDim.x) & 1);
+      TileMeta M[2];
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int64_t e = (2 * pair + t) * TM + S.row;
+        M[t].live = e < total;
+        M[t].ray = M[t].live ? (int)(e / p.S) : 0;
+        M[t].si = M[t].live ? (int)(e - (int64_t)M[t].ray * p.S) : 0;
+      }
+#pragma unroll 1
+      for (int si = 0; si < P.n_slots; ++si) {
+        const T2Slot sl = P.slots[si];
+        if (sl.tile == 0) epi_event<0>(S, sl.layer, sl.half, M[0], parity, stash0, acc_phase[0], sigma_part[0]);
+        else epi_event<1>(S, sl.layer, sl.half, M[1], parity, stash1, acc_phase[1], sigma_part[1]);
+      }
+    }
+  }
+
+  // ---- teardown ----
+  tc_fence_before();
+  __syncthreads();
+  if (warp == T2_MMA_WARP) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace
+
+int onerf_launch_field_bf16_two_tile(onerf_ctx* ctx, const FieldParams& fp, cudaStream_t stream) {
+  const PackLayout& L = fp.L;
+  T2Params P;
+  memset(&P, 0, sizeof(P));
+  P.f = fp;
+  const int xs = L.KX / 32, xo = L.KO / 32;
+  int n = 0;
+  auto add = [&](int gemm, int nx, int nh, int epi, int branch, int rc_base) {
+    T2Layer& t = P.layers[n++];
+    t.N = L.g[gemm].N; t.nhalf = t.N > 128 ? 2 : 1;
+    t.nslab_x = nx; t.nslab_h = nh; t.epi = epi; t.branch = branch; t.rc_base = rc_base;
+    t.writes_h = epi != EPI_DIR;
+    t.img_off = L.g[gemm].img_off; t.bias_off = L.g[gemm].bias_off;
+    int ng = 0;
+    auto emit = [&](int count, int from_h) {
+      for (int o = 0; o < count; o += T2_STAGE_SLABS) {
+        const int c = (count - o < T2_STAGE_SLABS) ? count - o : T2_STAGE_SLABS;
+        t.groups[ng++] = o | (c << 5) | (from_h << 8);
+      }
+    };
+    emit(nx, 0);
+    t.n_xgroups = ng;
+    emit(nh, 1);
+    t.ngroups = ng;
+  };
+  if (fp.want_scene) {
+    add(G_S0, xs, 0, EPI_HIDDEN, 0, 0);
+    add(G_S1, 0, 8, EPI_HIDDEN, 0, 0);
+    add(G_S2, 0, 8, EPI_HIDDEN, 0, 0);
+    add(G_S3, 0, 8, EPI_HIDDEN, 0, 0);
+    add(G_S4, xs, 8, EPI_HIDDEN, 0, 0);
+    add(G_S5, 0, 8, EPI_HIDDEN, 0, 0);
+    add(G_S6, 0, 8, EPI_HIDDEN, 0, 0);
+    add(G_S7, 0, 8, EPI_HIDDEN_SIGMA, 0, 0);
+    add(G_SFIN, 0, 8, EPI_FINAL, 0, 0);
+    add(G_SDIR, 0, 8, EPI_DIR, 0, RC_SDIR);
+  }
+  if (fp.want_object) {
+    add(G_O0, xo, 0, EPI_HIDDEN_RC, 1, RC_OL0);
+    add(G_O1, 0, 4, EPI_HIDDEN, 1, 0);
+    add(G_O2, xo, 4, EPI_HIDDEN_RC, 1, RC_OL2);
+    add(G_O3, 0, 4, EPI_HIDDEN_SIGMA, 1, 0);
+    add(G_OFIN, 0, 4, EPI_FINAL, 1, 0);
+    add(G_ODIR, 0, 4, EPI_DIR, 1, RC_ODIR);
+  }
+  P.n_layers = n;
+  // slots of one tile pair
+  int ns = 0, nx = 0;
+  auto slot = [&](int tile, int layer, int half, int flags) {
+    P.slots[ns].tile = (uint8_t)tile; P.slots[ns].layer = (uint8_t)layer; P.slots[ns].half = (uint8_t)half;
+    P.slots[ns].flags = (uint8_t)flags;
+    ++ns;
+  };
+  for (int l = 0; l < n; ++l) {
+    const T2Layer& t = P.layers[l];
+    const int wait_h = t.nslab_h > 0 ? SLOT_WAIT_H : 0;
+    if (t.nslab_x > 0) {
+      P.xuse_full[nx++] = t.branch ? 1 : 0;
+      // X-fed: the tile keeps XS for all its slots of the layer
+      for (int tile = 0; tile < 2; ++tile) {
+        if (t.nhalf == 2) {
+          slot(tile, l, 0, wait_h | SLOT_WAIT_XS);
+          slot(tile, l, 1, SLOT_XS_RELEASE);
+        } else {
+          slot(tile, l, 0, wait_h | SLOT_WAIT_XS | SLOT_XS_RELEASE);
+        }
+      }
+    } else if (t.nhalf == 2) {
+      slot(0, l, 0, wait_h); slot(1, l, 0, wait_h); slot(0, l, 1, 0); slot(1, l, 1, 0);
+    } else {
+      slot(0, l, 0, wait_h); slot(1, l, 0, wait_h);
+    }
+  }
+  P.n_slots = ns;
+  P.n_xuse = nx;
+  const int64_t total = (int64_t)fp.n_rays * fp.S;
+  const int64_t tiles = (total + TM - 1) / TM, pairs = (tiles + 1) / 2;
+  const int blocks = (int)(pairs < ctx->num_sms ? pairs : ctx->num_sms);
+  const size_t smem = T2_SMEM_BYTES;
+  ONERF_CUDA(cudaFuncSetAttribute(field_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  field_tc2_kernel<<<blocks, T2_THREADS, smem, stream>>>(P);
+  ONERF_LAUNCH_CHECK(ctx);
+  return ONERF_OK;
+}
