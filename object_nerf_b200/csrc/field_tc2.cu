@@ -5,10 +5,12 @@
 // behind its own MMAs (profiles/r01_experiments.md).  Here a CTA owns TWO 128-row tiles (A, B) that walk the layer
 // program in lockstep, half a layer apart: while the 16 epilogue warps drain a layer half of one tile, the tensor pipe
 // runs the same layer half of the other.
-//   slot order per two-half layer l :  (A,l,h0) (B,l,h0) (A,l,h1) (B,l,h1)      [X-fed: (A,h0) (A,h1) (B,h0) (B,h1)]
-//   TMEM (512 columns)              :  tile t: accumulator [256 t, +128), activations [256 t + 128, +128) IN PLACE
-//                                      (bf16 pairs): the outputs of half 0 wait in 16 registers per thread until the
-//                                      MMAs of half 1 have read the old activations
+//   slot order per two-half layer l :  (A,l,h0) (A,l,h1) (B,l,h0) (B,l,h1);  one-half layers (N <= 128): (A,l) (B,l)
+//   TMEM (512 columns)              :  two 128-column accumulators SHARED by the tiles (half h of a two-half layer uses
+//                                      accumulator h, a one-half layer of tile t uses accumulator t), so consecutive slots
+//                                      never wait for each other's epilogue; activations of tile t at [256 + 128 t, +128)
+//                                      IN PLACE (bf16 pairs): the outputs of half 0 wait in 16 registers per thread until
+//                                      the MMAs of half 1 have read the old activations
 //   shared memory                   :  ONE 96 KB buffer XS for the encoded input X (the A operand of the four X-fed layers),
 //                                      regenerated from 27 raw features per sample (24 trilinear voxel channels + xyz,
 //                                      kept in shared memory for both tiles) by four dedicated encode warps each time a
@@ -18,8 +20,8 @@
 //   (warps 18-19 idle: they complete the control warpgroup)        positional encoding into XS
 // Registers are re-divided between the warpgroups with setmaxnreg (epilogue 104: two 16-register stashes; control 40;
 // encode 56).
-// mbarriers: full / empty (ring), acc_ready[t] (MMA -> epilogue), acc_free[t] (epilogue has loaded the accumulator: the
-// tile's next MMAs may overwrite it), h_ready[t] (a layer's activations are written), xs_ready / xs_free (XS hand-over).
+// mbarriers: full / empty (ring), acc_ready[a] (MMA -> epilogue), acc_free[a] (the epilogue has loaded accumulator a: the
+// next MMAs may overwrite it), h_ready[t] (a layer's activations of tile t are written), xs_ready / xs_free (XS hand-over).
 // Arithmetic is that of the one-tile kernel (same K order, same epilogue math): results are bit-identical to it.
 //
 // Reference semantics: models/rendering.py:85-137, models/nerf_model.py:97-152,
@@ -65,7 +67,7 @@ struct T2Layer {
   int groups[T2_MAX_GROUPS];   // bits [0,5) first slab (inside X or H), [5,8) slab count (1..3), bit 8: from H
 };
 struct T2Slot {
-  uint8_t tile, layer, half, flags;
+  uint8_t tile, layer, half, flags;   // flags: SlotFlags | accumulator index << 4
 };
 struct T2Params {
   FieldParams f;
@@ -160,10 +162,10 @@ struct TileMeta {            // per tile of the current pair
   bool live;
 };
 
-// One epilogue event: layer `l`, half `h` of tile T.  `stash`: the packed outputs of half 0 of a two-half layer.
-template <int T>
-__device__ __forceinline__ void epi_event(const EpiShared& S, int l, int h, const TileMeta& M, int parity, uint32_t (&stash)[16],
-                                          uint32_t& acc_phase, float& sigma_part) {
+// One epilogue event: layer `l`, half `h` of tile `T`, accumulator `A`.  `stash`: the packed outputs of half 0 of a two-half
+// layer (the slots of a tile's layer are consecutive: one stash serves both tiles).
+__device__ __forceinline__ void epi_event(const EpiShared& S, int T, int A, int l, int h, const TileMeta& M, int parity,
+                                          uint32_t (&stash)[16], uint32_t& acc_bits, float& sigma_part) {
   const T2Params& P = *S.P;
   const T2Layer& Ly = P.layers[l];
   const FieldParams& p = P.f;
@@ -173,27 +175,31 @@ __device__ __forceinline__ void epi_event(const EpiShared& S, int l, int h, cons
   const uint32_t bar_acc_ready = S.sbase + OFF_BAR + 16 * T2_NSTAGE, bar_acc_free = bar_acc_ready + 16, bar_h_ready = bar_acc_free + 16;
   const int HW = Ly.N >> (Ly.nhalf - 1);       // 128, or 64 for the object dir layer
   const int n = h * HW + S.cq * (HW >> 2);     // first output column of this thread
-  const uint32_t acc_addr = S.lane_taddr + (uint32_t)(T * 256 + S.cq * (HW >> 2));
-  const uint32_t h_addr = S.lane_taddr + (uint32_t)(T * 256 + 128);
+  const uint32_t acc_addr = S.lane_taddr + (uint32_t)(A * 128 + S.cq * (HW >> 2));
+  const uint32_t h_addr = S.lane_taddr + (uint32_t)(256 + T * 128);
   const float* rc = p.ray_const + (int64_t)M.ray * ONERF_RAY_CONST_FLOATS;
-  mbar_wait(bar_acc_ready + 8 * T, acc_phase);
-  acc_phase ^= 1;
+  mbar_wait(bar_acc_ready + 8 * A, (acc_bits >> A) & 1u);
+  acc_bits ^= 1u << A;
   tc_fence_after();
-  uint32_t v[32];
-  if (HW == 128) { tmem_ld16(acc_addr, v); tmem_ld16(acc_addr + 16, v + 16); }
-  else tmem_ld16(acc_addr, v);
-  tmem_ld_wait();
-  // the accumulator is in registers: the tile's next MMAs may overwrite it
-  tc_fence_before();
-  __syncwarp();
-  if (S.lane == 0) mbar_arrive(bar_acc_free + 8 * T);
-  uint32_t pk[16];
+  // the accumulator is consumed in batches of 16 columns (16 live registers instead of 32); after the last load it is
+  // handed back: the tile's next MMAs may overwrite it
+  auto release_acc = [&]() {
+    tc_fence_before();
+    __syncwarp();
+    if (S.lane == 0) mbar_arrive(bar_acc_free + 8 * A);
+  };
+  const int nbatch = HW >> 6;                  // 2 (32 columns per thread) or 1 (the 64-wide object dir layer)
   const float* bias = bias_tab + l * 256 + n;
   if (Ly.epi == EPI_DIR) {
     const float* headw = Pf + (Ly.branch ? p.L.orgb_w : p.L.rgb_w) + n;
     float part0 = 0.0f, part1 = 0.0f, part2 = 0.0f;
-    if (HW == 128) math_dir<32>(v, rc + Ly.rc_base + n, headw, Ly.N, part0, part1, part2);
-    else math_dir<16>(v, rc + Ly.rc_base + n, headw, Ly.N, part0, part1, part2);
+    for (int bt = 0; bt < nbatch; ++bt) {
+      uint32_t v[16];
+      tmem_ld16(acc_addr + 16 * bt, v);
+      tmem_ld_wait();
+      if (bt == nbatch - 1) release_acc();
+      math_dir<16>(v, rc + Ly.rc_base + n + 16 * bt, headw + 16 * bt, Ly.N, part0, part1, part2);
+    }
     // combine the four column quarters of this row through shared memory, finish the heads, write out
     float* sc = scratch + (S.row * 4 + S.cq) * 4;
     sc[0] = sigma_part; sc[1] = part0; sc[2] = part1; sc[3] = part2;
@@ -215,32 +221,75 @@ __device__ __forceinline__ void epi_event(const EpiShared& S, int l, int h, cons
     asm volatile("bar.sync 1, %0;" ::"n"(T2_EPI_THREADS) : "memory");  // scratch reusable
     return;
   }
-  switch (Ly.epi) {
-    case EPI_HIDDEN: math_hidden<32, true, false>(v, bias, pk); break;
-    case EPI_HIDDEN_RC: math_hidden<32, true, true>(v, rc + Ly.rc_base + n, pk); break;
-    case EPI_FINAL: math_hidden<32, false, false>(v, bias, pk); break;
-    default: {   // EPI_HIDDEN_SIGMA
-      const float* headw = Pf + (Ly.branch ? p.L.osigma_w : p.L.sigma_w) + n;
-      const float part = math_hidden_sigma<32>(v, bias, headw, pk);
-      sigma_part = (h == 0) ? part : sigma_part + part;
-    } break;
-  }
-  if (Ly.nhalf == 2 && h == 0) {
+  // every non-dir layer half is 128 wide: 32 columns per thread, in two batches of 16
+  float part = 0.0f;
+  auto run = [&](uint32_t (&out)[16]) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) stash[j] = pk[j];
+    for (int bt = 0; bt < 2; ++bt) {
+      uint32_t v[16];
+      tmem_ld16(acc_addr + 16 * bt, v);
+      tmem_ld_wait();
+      if (bt == 1) release_acc();
+      switch (Ly.epi) {
+        case EPI_HIDDEN: math_hidden<16, true, false>(v, bias + 16 * bt, out + 8 * bt); break;
+        case EPI_HIDDEN_RC: math_hidden<16, true, true>(v, rc + Ly.rc_base + n + 16 * bt, out + 8 * bt); break;
+        case EPI_FINAL: math_hidden<16, false, false>(v, bias + 16 * bt, out + 8 * bt); break;
+        default:   // EPI_HIDDEN_SIGMA
+          part += math_hidden_sigma<16>(v, bias + 16 * bt, Pf + (Ly.branch ? p.L.osigma_w : p.L.sigma_w) + n + 16 * bt, out + 8 * bt);
+          break;
+      }
+    }
+  };
+  if (Ly.nhalf == 2 && h == 0) {
+    run(stash);                                  // kept in registers until the MMAs of half 1 have read the old activations
+    if (Ly.epi == EPI_HIDDEN_SIGMA) sigma_part = part;
     return;
   }
-  // all MMAs of this layer have completed (this half's accumulator was ready): overwrite the activations in place
-  if (Ly.nhalf == 2) {
-    tmem_st16(h_addr + (uint32_t)(S.cq * 16), stash);
-    tmem_st16(h_addr + (uint32_t)(64 + S.cq * 16), pk);
-  } else {
-    tmem_st16(h_addr + (uint32_t)(S.cq * 16), pk);
-  }
+  // this half's accumulator is complete, so every MMA of the layer has finished reading the old activations: overwrite them
+  // in place, half 0 first (its registers are free before this half's outputs are formed)
+  if (Ly.nhalf == 2) tmem_st16(h_addr + (uint32_t)(S.cq * 16), stash);
+  uint32_t pk[16];
+  run(pk);
+  if (Ly.epi == EPI_HIDDEN_SIGMA) sigma_part = (Ly.nhalf == 2) ? sigma_part + part : part;
+  tmem_st16(h_addr + (uint32_t)((Ly.nhalf == 2 ? 64 : 0) + S.cq * 16), pk);
   tmem_st_wait();
   tc_fence_before();
   __syncwarp();
   if (S.lane == 0) mbar_arrive(bar_h_ready + 8 * T);
+}
+
+// Trilinear gather of one row's 27 raw features (24 voxel channels, x, y, z) and its mute flags.  Not inlined: it is called
+// from three places of the encode warps' loop and is off the critical path (it prefetches the NEXT tile pair).
+__device__ __noinline__ void gather_tile(const FieldParams& p, const GridView& g, float* F, uint8_t* mute_out, int64_t e,
+                                         int64_t total) {
+  const bool live = e < total;
+  const int ray = live ? (int)(e / p.S) : 0;
+  const int si = live ? (int)(e - (int64_t)ray * p.S) : 0;
+  const float* rr = p.rays + (int64_t)ray * 8;
+  const float zz = live ? __ldg(p.z + (int64_t)ray * p.z_stride + si) : 0.0f;
+  float x = fmaf(__ldg(rr + 3), zz, __ldg(rr + 0));
+  float y = fmaf(__ldg(rr + 4), zz, __ldg(rr + 1));
+  float z = fmaf(__ldg(rr + 5), zz, __ldg(rr + 2));
+  if (p.xyz && live) {
+    const float* qq = p.xyz + ((int64_t)ray * p.S + si) * 3;
+    x = __ldg(qq); y = __ldg(qq + 1); z = __ldg(qq + 2);
+  }
+  if (!live) { x = 0.f; y = 0.f; z = 0.f; }
+  int mute = 0;  // bit 0: scene sigma muted, bit 1: object sigma muted
+  if (live && p.mute_zero_rays && __ldg(p.z + (int64_t)ray * p.z_stride + (p.S - 1)) == 0.0f) mute = 3;
+  if (live && mute == 0 && p.n_boxes > 0 && point_in_boxes(p.boxes, p.n_boxes, x, y, z)) mute = 1;
+  *mute_out = (uint8_t)mute;
+  float f[8];
+  voxel_trilinear<0, 8, false>(g, x, y, z, f);
+#pragma unroll
+  for (int c = 0; c < 8; ++c) F[c * 128] = f[c];
+  voxel_trilinear<8, 8, false>(g, x, y, z, f);
+#pragma unroll
+  for (int c = 0; c < 8; ++c) F[(8 + c) * 128] = f[c];
+  voxel_trilinear<16, 8, false>(g, x, y, z, f);
+#pragma unroll
+  for (int c = 0; c < 8; ++c) F[(16 + c) * 128] = f[c];
+  F[24 * 128] = x; F[25 * 128] = y; F[26 * 128] = z;
 }
 
 __global__ void __launch_bounds__(T2_THREADS, 1) field_tc2_kernel(const __grid_constant__ T2Params P) {
@@ -269,7 +318,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) field_tc2_kernel(const __grid_c
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
     }
-    for (int t = 0; t < 2; ++t) {
+    for (int t = 0; t < 2; ++t) {    // two accumulators, two tiles
       mbar_init(bar_acc_ready + 8 * t, 1);
       mbar_init(bar_acc_free + 8 * t, T2_EPI_THREADS / 32);
       mbar_init(bar_h_ready + 8 * t, T2_EPI_THREADS / 32);
@@ -338,11 +387,12 @@ __global__ void __launch_bounds__(T2_THREADS, 1) field_tc2_kernel(const __grid_c
         const uint32_t idesc = make_idesc(Ly.N >> (Ly.nhalf - 1));
         const uint32_t half_bytes = ((uint32_t)Ly.N * 64u) >> (Ly.nhalf - 1);
         const uint32_t hb16 = half_bytes >> 4;
-        const uint32_t d_tmem = tmem_base + (uint32_t)(t * 256);
-        const uint32_t h_tmem = tmem_base + (uint32_t)(t * 256 + 128);
-        // the epilogue of the tile's previous slot holds the accumulator in registers
-        mbar_wait(bar_acc_free + 8 * t, (free_bits >> t) & 1u);
-        free_bits ^= 1u << t;
+        const int acc = sl.flags >> 4;
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 128);
+        const uint32_t h_tmem = tmem_base + (uint32_t)(256 + t * 128);
+        // the epilogue of the accumulator's previous user has loaded it into registers
+        mbar_wait(bar_acc_free + 8 * acc, (free_bits >> acc) & 1u);
+        free_bits ^= 1u << acc;
         if (sl.flags & SLOT_WAIT_H) {   // the previous layer's activations are written
           mbar_wait(bar_h_ready + 8 * t, (h_bits >> t) & 1u);
           h_bits ^= 1u << t;
@@ -388,7 +438,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) field_tc2_kernel(const __grid_c
             }
             umma_commit(bar_empty + 8 * stage);
             if (gi == Ly.n_xgroups - 1 && (sl.flags & SLOT_XS_RELEASE)) umma_commit(bar_xs_free);
-            if (gi == Ly.ngroups - 1) umma_commit(bar_acc_ready + 8 * t);
+            if (gi == Ly.ngroups - 1) umma_commit(bar_acc_ready + 8 * acc);
           }
           __syncwarp();
           if (++stage == T2_NSTAGE) { stage = 0; phase ^= 1; }
@@ -399,38 +449,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1) field_tc2_kernel(const __grid_c
     // =============================== encode warps: raw features and XS ===============================
     const int row = (warp - T2_ENC_WARP0) * 32 + lane;
     const GridView g = load_grid_view(p.grid);
-    // trilinear gather of one tile's 27 raw features per row + the mute flags of the row
     auto gather = [&](int t, int64_t tile, int parity) {
-      const int64_t e = tile * TM + row;
-      const bool live = e < total;
-      const int ray = live ? (int)(e / p.S) : 0;
-      const int si = live ? (int)(e - (int64_t)ray * p.S) : 0;
-      const float* rr = p.rays + (int64_t)ray * 8;
-      const float zz = live ? __ldg(p.z + (int64_t)ray * p.z_stride + si) : 0.0f;
-      float x = fmaf(__ldg(rr + 3), zz, __ldg(rr + 0));
-      float y = fmaf(__ldg(rr + 4), zz, __ldg(rr + 1));
-      float z = fmaf(__ldg(rr + 5), zz, __ldg(rr + 2));
-      if (p.xyz && live) {
-        const float* qq = p.xyz + ((int64_t)ray * p.S + si) * 3;
-        x = __ldg(qq); y = __ldg(qq + 1); z = __ldg(qq + 2);
-      }
-      if (!live) { x = 0.f; y = 0.f; z = 0.f; }
-      int mute = 0;  // bit 0: scene sigma muted, bit 1: object sigma muted
-      if (live && p.mute_zero_rays && __ldg(p.z + (int64_t)ray * p.z_stride + (p.S - 1)) == 0.0f) mute = 3;
-      if (live && mute == 0 && p.n_boxes > 0 && point_in_boxes(p.boxes, p.n_boxes, x, y, z)) mute = 1;
-      mute_tab[(parity * 2 + t) * 128 + row] = (uint8_t)mute;
-      float* F = feat + (size_t)t * T2_NF * 128 + row;
-      float f[8];
-      voxel_trilinear<0, 8, false>(g, x, y, z, f);
-#pragma unroll
-      for (int c = 0; c < 8; ++c) F[c * 128] = f[c];
-      voxel_trilinear<8, 8, false>(g, x, y, z, f);
-#pragma unroll
-      for (int c = 0; c < 8; ++c) F[(8 + c) * 128] = f[c];
-      voxel_trilinear<16, 8, false>(g, x, y, z, f);
-#pragma unroll
-      for (int c = 0; c < 8; ++c) F[(16 + c) * 128] = f[c];
-      F[24 * 128] = x; F[25 * 128] = y; F[26 * 128] = z;
+      gather_tile(p, g, feat + (size_t)t * T2_NF * 128 + row, mute_tab + (parity * 2 + t) * 128 + row, tile * TM + row, total);
     };
     uint32_t regen = 0;   // regenerations of XS so far (the r-th one waits for the release of the (r-1)-th)
     bool first_pair = true;
@@ -477,10 +497,10 @@ __global__ void __launch_bounds__(T2_THREADS, 1) field_tc2_kernel(const __grid_c
     const int q = warp & 3;
     S.cq = warp >> 2; S.lane = lane; S.row = q * 32 + lane;
     S.lane_taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-    uint32_t acc_phase[2] = {0, 0};
-    uint32_t stash0[16], stash1[16];
-    float sigma_part[2] = {0.0f, 0.0f};
-    // nothing holds the accumulators before the very first slots
+    uint32_t acc_bits = 0;
+    uint32_t stash[16];
+    float sigma_a = 0.0f, sigma_b = 0.0f;
+    // nothing holds the two accumulators before their first use
     if (lane == 0) {
       mbar_arrive(bar_acc_free);
       mbar_arrive(bar_acc_free + 8);
@@ -498,8 +518,12 @@ __global__ void __launch_bounds__(T2_THREADS, 1) field_tc2_kernel(const __grid_c
 #pragma unroll 1
       for (int si = 0; si < P.n_slots; ++si) {
         const T2Slot sl = P.slots[si];
-        if (sl.tile == 0) epi_event<0>(S, sl.layer, sl.half, M[0], parity, stash0, acc_phase[0], sigma_part[0]);
-        else epi_event<1>(S, sl.layer, sl.half, M[1], parity, stash1, acc_phase[1], sigma_part[1]);
+        const int T = sl.tile;
+        TileMeta Mt;
+        Mt.ray = T ? M[1].ray : M[0].ray; Mt.si = T ? M[1].si : M[0].si; Mt.live = T ? M[1].live : M[0].live;
+        float sg = T ? sigma_b : sigma_a;
+        epi_event(S, T, sl.flags >> 4, sl.layer, sl.half, Mt, parity, stash, acc_bits, sg);
+        if (T) sigma_b = sg; else sigma_a = sg;
       }
     }
   }
@@ -568,21 +592,16 @@ int onerf_launch_field_bf16_two_tile(onerf_ctx* ctx, const FieldParams& fp, cuda
   for (int l = 0; l < n; ++l) {
     const T2Layer& t = P.layers[l];
     const int wait_h = t.nslab_h > 0 ? SLOT_WAIT_H : 0;
-    if (t.nslab_x > 0) {
-      P.xuse_full[nx++] = t.branch ? 1 : 0;
-      // X-fed: the tile keeps XS for all its slots of the layer
-      for (int tile = 0; tile < 2; ++tile) {
-        if (t.nhalf == 2) {
-          slot(tile, l, 0, wait_h | SLOT_WAIT_XS);
-          slot(tile, l, 1, SLOT_XS_RELEASE);
-        } else {
-          slot(tile, l, 0, wait_h | SLOT_WAIT_XS | SLOT_XS_RELEASE);
-        }
+    const bool xfed = t.nslab_x > 0;
+    if (xfed) P.xuse_full[nx++] = t.branch ? 1 : 0;
+    // a tile's slots of a layer are consecutive; an X-fed layer keeps XS for all of them
+    for (int tile = 0; tile < 2; ++tile) {
+      if (t.nhalf == 2) {
+        slot(tile, l, 0, wait_h | (xfed ? SLOT_WAIT_XS : 0) | (0 << 4));
+        slot(tile, l, 1, (xfed ? SLOT_XS_RELEASE : 0) | (1 << 4));
+      } else {
+        slot(tile, l, 0, wait_h | (xfed ? (SLOT_WAIT_XS | SLOT_XS_RELEASE) : 0) | (tile << 4));
       }
-    } else if (t.nhalf == 2) {
-      slot(0, l, 0, wait_h); slot(1, l, 0, wait_h); slot(0, l, 1, 0); slot(1, l, 1, 0);
-    } else {
-      slot(0, l, 0, wait_h); slot(1, l, 0, wait_h);
     }
   }
   P.n_slots = ns;
