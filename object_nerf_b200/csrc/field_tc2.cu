@@ -258,9 +258,10 @@ __device__ __forceinline__ void epi_event(const EpiShared& S, int T, int A, int 
   if (S.lane == 0) mbar_arrive(bar_h_ready + 8 * T);
 }
 
-// Trilinear gather of one row's 27 raw features (24 voxel channels, x, y, z) and its mute flags.  Not inlined: it is called
-// from three places of the encode warps' loop and is off the critical path (it prefetches the NEXT tile pair).
-__device__ __noinline__ void gather_tile(const FieldParams& p, const GridView& g, float* F, uint8_t* mute_out, int64_t e,
+// Trilinear gather of one row's 27 raw features (24 voxel channels, x, y, z) and its mute flags.  Off the critical path: it
+// prefetches the NEXT tile pair.  Inlined at ONE call site: a separately compiled function would not know the register
+// budget setmaxnreg left to the encode warps.
+__device__ __forceinline__ void gather_tile(const FieldParams& p, const GridView& g, float* F, uint8_t* mute_out, int64_t e,
                                          int64_t total) {
   const bool live = e < total;
   const int ray = live ? (int)(e / p.S) : 0;
@@ -453,40 +454,38 @@ __global__ void __launch_bounds__(T2_THREADS, 1) field_tc2_kernel(const __grid_c
       gather_tile(p, g, feat + (size_t)t * T2_NF * 128 + row, mute_tab + (parity * 2 + t) * 128 + row, tile * TM + row, total);
     };
     uint32_t regen = 0;   // regenerations of XS so far (the r-th one waits for the release of the (r-1)-th)
-    bool first_pair = true;
-    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-      const int parity = (int)(((pair - blockIdx.x) / gridDim.x) & 1);
-      if (first_pair) {
-        gather(0, 2 * pair, parity);
-        gather(1, 2 * pair + 1, parity);
-        first_pair = false;
-      }
-      for (int u = 0; u < P.n_xuse; ++u) {
+    // The loop starts one (virtual) pair early: a virtual pair has no X to produce, it only prefetches the first real pair.
+    for (int64_t pair = (int64_t)blockIdx.x - (int64_t)gridDim.x; pair < n_pairs; pair += gridDim.x) {
+      const bool real = pair >= 0;
+      const int nu = real ? P.n_xuse : 1;
+      const int64_t next = pair + gridDim.x;
+      const int next_parity = (int)(((next - blockIdx.x) / gridDim.x) & 1);
+      for (int u = 0; u < nu; ++u) {
         for (int t = 0; t < 2; ++t) {
-          if (regen > 0) mbar_wait(bar_xs_free, (regen - 1) & 1);   // every MMA that read the previous X has completed
-          const float* F = feat + (size_t)t * T2_NF * 128 + row;
-          float f[8];
+          if (real) {
+            if (regen > 0) mbar_wait(bar_xs_free, (regen - 1) & 1);   // every MMA that read the previous X has completed
+            const float* F = feat + (size_t)t * T2_NF * 128 + row;
+            float f[8];
 #pragma unroll
-          for (int c = 0; c < 8; ++c) f[c] = F[c * 128];
-          pe8_to_chunks(sX, row, 0, 2, f);          // scene channels 0-7 : chunks 0, 2, 4, ...
+            for (int c = 0; c < 8; ++c) f[c] = F[c * 128];
+            pe8_to_chunks(sX, row, 0, 2, f);          // scene channels 0-7 : chunks 0, 2, 4, ...
 #pragma unroll
-          for (int c = 0; c < 8; ++c) f[c] = F[(8 + c) * 128];
-          pe8_to_chunks(sX, row, 1, 2, f);          // scene channels 8-15: chunks 1, 3, 5, ...
-          pe_xyz_to_chunks(sX, row, 26, F[24 * 128], F[25 * 128], F[26 * 128]);   // columns 208..271
-          if (P.xuse_full[u]) {
+            for (int c = 0; c < 8; ++c) f[c] = F[(8 + c) * 128];
+            pe8_to_chunks(sX, row, 1, 2, f);          // scene channels 8-15: chunks 1, 3, 5, ...
+            pe_xyz_to_chunks(sX, row, 26, F[24 * 128], F[25 * 128], F[26 * 128]);   // columns 208..271
+            if (P.xuse_full[u]) {
 #pragma unroll
-            for (int c = 0; c < 8; ++c) f[c] = F[(16 + c) * 128];
-            pe8_to_chunks(sX, row, 34, 1, f);       // object voxel block starts at column 272 = chunk 34
-            st_chunk(a_chunk_addr(sX, row, 47), 0u, 0u, 0u, 0u);  // columns 376..383
+              for (int c = 0; c < 8; ++c) f[c] = F[(16 + c) * 128];
+              pe8_to_chunks(sX, row, 34, 1, f);       // object voxel block starts at column 272 = chunk 34
+              st_chunk(a_chunk_addr(sX, row, 47), 0u, 0u, 0u, 0u);  // columns 376..383
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_xs_ready);
+            ++regen;
           }
-          fence_async_smem();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_xs_ready);
-          ++regen;
-          if (u == P.n_xuse - 1) {   // this tile's features are no longer needed: fetch the next pair's
-            const int64_t next = pair + gridDim.x;
-            if (next < n_pairs) gather(t, 2 * next + t, parity ^ 1);
-          }
+          // this tile's features are no longer needed: fetch the next pair's
+          if (u == nu - 1 && next < n_pairs) gather(t, 2 * next + t, next_parity);
         }
       }
     }
