@@ -18,7 +18,7 @@
 //   warps 0-15  epilogue (both tiles, alternating)    warp 16  weight producer (cp.async.bulk)
 //   warp 17     tcgen05.mma issuer (owns TMEM)        warps 20-23  encode: trilinear gather of the NEXT tile pair,
 //   (warps 18-19 idle: they complete the control warpgroup)        positional encoding into XS
-// Registers are re-divided between the warpgroups with setmaxnreg (epilogue 104: two 16-register stashes; control 40;
+// Registers are re-divided between the warpgroups with setmaxnreg (epilogue 96; control 40;
 // encode 56).
 // mbarriers: full / empty (ring), acc_ready[a] (MMA -> epilogue), acc_free[a] (the epilogue has loaded accumulator a: the
 // next MMAs may overwrite it), h_ready[t] (a layer's activations of tile t are written), xs_ready / xs_free (XS hand-over).
@@ -49,7 +49,8 @@ constexpr int T2_EPI_THREADS = 512;
 // warpgroups (setmaxnreg works per group of 4 warps): 0-3 epilogue, 4 = {producer, MMA, 2 idle}, 5 = encode
 constexpr int T2_PRODUCER_WARP = 16, T2_MMA_WARP = 17, T2_ENC_WARP0 = 20, T2_ENC_WARPS = 4;
 constexpr int T2_THREADS = 32 * (T2_ENC_WARP0 + T2_ENC_WARPS);   // 768: 80 registers per thread at launch
-constexpr int T2_REGS_EPI = 104, T2_REGS_CTRL = 40, T2_REGS_ENC = 56;   // 512 x 104 + 128 x 40 + 128 x 56 = 65 536
+// setmaxnreg moves registers inside the pool the CTA was LAUNCHED with (768 threads x 80), not the whole register file
+constexpr int T2_REGS_EPI = 96, T2_REGS_CTRL = 40, T2_REGS_ENC = 56;   // 512 x 96 + 128 x 40 + 128 x 56 = 61 440 = 768 x 80
 constexpr int T2_NF = 27;                     // raw features per sample: 24 trilinear channels, x, y, z
 constexpr float kLeaky = 0.01f;
 
