@@ -78,7 +78,14 @@ struct T2Params {
   int n_slots;
   int n_xuse;                       // X-fed layers per tile, in program order
   int xuse_full[T2_MAX_XUSE];       // 1: the layer reads all 384 columns (object branch), 0: the first 288 (scene)
+  long long* timeline;              // -DONERF_TIMELINE: clock64() stamps of block 0, second tile pair (tools/timeline2.py)
 };
+
+#ifdef ONERF_TIMELINE
+#define T2_STAMP(cond, idx) do { if ((cond) && P.timeline && blockIdx.x == 0 && pair == (int64_t)gridDim.x) P.timeline[idx] = clock64(); } while (0)
+#else
+#define T2_STAMP(cond, idx) do { } while (0)
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // epilogue math (same operations as field_tc.cu)
@@ -390,6 +397,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) field_tc2_kernel(const __grid_c
         const uint32_t half_bytes = ((uint32_t)Ly.N * 64u) >> (Ly.nhalf - 1);
         const uint32_t hb16 = half_bytes >> 4;
         const int acc = sl.flags >> 4;
+        T2_STAMP(lane == 0, si * 8 + 0);
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 128);
         const uint32_t h_tmem = tmem_base + (uint32_t)(256 + t * 128);
         // the epilogue of the accumulator's previous user has loaded it into registers
@@ -412,6 +420,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) field_tc2_kernel(const __grid_c
           }
           mbar_wait(bar_full + 8 * stage, phase);
           tc_fence_after();
+          T2_STAMP(lane == 0 && gi == 0, si * 8 + 1);
           if (elect_one()) {
             uint32_t accum = accum0;
             if (!from_h) {
@@ -443,6 +452,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) field_tc2_kernel(const __grid_c
             if (gi == Ly.ngroups - 1) umma_commit(bar_acc_ready + 8 * acc);
           }
           __syncwarp();
+          T2_STAMP(lane == 0 && gi == Ly.ngroups - 1, si * 8 + 2);
           if (++stage == T2_NSTAGE) { stage = 0; phase ^= 1; }
         }
       }
@@ -464,7 +474,9 @@ __global__ void __launch_bounds__(T2_THREADS, 1) field_tc2_kernel(const __grid_c
       for (int u = 0; u < nu; ++u) {
         for (int t = 0; t < 2; ++t) {
           if (real) {
+            T2_STAMP(threadIdx.x == T2_ENC_WARP0 * 32, 512 + (u * 2 + t) * 4 + 0);
             if (regen > 0) mbar_wait(bar_xs_free, (regen - 1) & 1);   // every MMA that read the previous X has completed
+            T2_STAMP(threadIdx.x == T2_ENC_WARP0 * 32, 512 + (u * 2 + t) * 4 + 1);
             const float* F = feat + (size_t)t * T2_NF * 128 + row;
             float f[8];
 #pragma unroll
@@ -483,6 +495,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) field_tc2_kernel(const __grid_c
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_xs_ready);
+            T2_STAMP(threadIdx.x == T2_ENC_WARP0 * 32, 512 + (u * 2 + t) * 4 + 2);
             ++regen;
           }
           // this tile's features are no longer needed: fetch the next pair's
@@ -519,11 +532,13 @@ __global__ void __launch_bounds__(T2_THREADS, 1) field_tc2_kernel(const __grid_c
       for (int si = 0; si < P.n_slots; ++si) {
         const T2Slot sl = P.slots[si];
         const int T = sl.tile;
+        T2_STAMP(threadIdx.x == 0, si * 8 + 4);
         TileMeta Mt;
         Mt.ray = T ? M[1].ray : M[0].ray; Mt.si = T ? M[1].si : M[0].si; Mt.live = T ? M[1].live : M[0].live;
         float sg = T ? sigma_b : sigma_a;
         epi_event(S, T, sl.flags >> 4, sl.layer, sl.half, Mt, parity, stash, acc_bits, sg);
         if (T) sigma_b = sg; else sigma_a = sg;
+        T2_STAMP(threadIdx.x == 0, si * 8 + 5);
       }
     }
   }
@@ -536,11 +551,15 @@ __global__ void __launch_bounds__(T2_THREADS, 1) field_tc2_kernel(const __grid_c
 
 }  // namespace
 
+static long long* g_timeline2 = nullptr;
+extern "C" void onerf_debug_timeline2(void* dev_buf) { g_timeline2 = reinterpret_cast<long long*>(dev_buf); }
+
 int onerf_launch_field_bf16_two_tile(onerf_ctx* ctx, const FieldParams& fp, cudaStream_t stream) {
   const PackLayout& L = fp.L;
   T2Params P;
   memset(&P, 0, sizeof(P));
   P.f = fp;
+  P.timeline = g_timeline2;
   const int xs = L.KX / 32, xo = L.KO / 32;
   int n = 0;
   auto add = [&](int gemm, int nx, int nh, int epi, int branch, int rc_base) {
