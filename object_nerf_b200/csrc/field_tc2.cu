@@ -13,13 +13,12 @@
 //                                      the MMAs of half 1 have read the old activations
 //   shared memory                   :  ONE 96 KB buffer XS for the encoded input X (the A operand of the four X-fed layers),
 //                                      regenerated from 27 raw features per sample (24 trilinear voxel channels + xyz,
-//                                      kept in shared memory for both tiles) by four dedicated encode warps each time a
+//                                      kept in shared memory for both tiles) by two dedicated encode warps each time a
 //                                      tile reaches an X-fed layer; 3 x 24 KB weight ring; biases
 //   warps 0-15  epilogue (both tiles, alternating)    warp 16  weight producer (cp.async.bulk)
-//   warp 17     tcgen05.mma issuer (owns TMEM)        warps 20-23  encode: trilinear gather of the NEXT tile pair,
-//   (warps 18-19 idle: they complete the control warpgroup)        positional encoding into XS
-// Registers are re-divided between the warpgroups with setmaxnreg (epilogue 96; control 40;
-// encode 56).
+//   warp 17     tcgen05.mma issuer (owns TMEM)        warps 18-19  encode: trilinear gather of the NEXT tile pair,
+//                                                                  positional encoding into XS (two rows per thread)
+// Registers are re-divided between the warpgroups with setmaxnreg (epilogue 104, control / encode 64).
 // mbarriers: full / empty (ring), acc_ready[a] (MMA -> epilogue), acc_free[a] (the epilogue has loaded accumulator a: the
 // next MMAs may overwrite it), h_ready[t] (a layer's activations of tile t are written), xs_ready / xs_free (XS hand-over).
 // Arithmetic is that of the one-tile kernel (same K order, same epilogue math): results are bit-identical to it.
@@ -46,11 +45,12 @@ constexpr int T2_MAX_LAYERS = 16;
 constexpr int T2_MAX_SLOTS = 56;
 constexpr int T2_MAX_XUSE = 4;
 constexpr int T2_EPI_THREADS = 512;
-// warpgroups (setmaxnreg works per group of 4 warps): 0-3 epilogue, 4 = {producer, MMA, 2 idle}, 5 = encode
-constexpr int T2_PRODUCER_WARP = 16, T2_MMA_WARP = 17, T2_ENC_WARP0 = 20, T2_ENC_WARPS = 4;
-constexpr int T2_THREADS = 32 * (T2_ENC_WARP0 + T2_ENC_WARPS);   // 768: 80 registers per thread at launch
-// setmaxnreg moves registers inside the pool the CTA was LAUNCHED with (768 threads x 80), not the whole register file
-constexpr int T2_REGS_EPI = 96, T2_REGS_CTRL = 40, T2_REGS_ENC = 56;   // 512 x 96 + 128 x 40 + 128 x 56 = 61 440 = 768 x 80
+// warpgroups (setmaxnreg works per group of 4 warps): 0-3 epilogue, 4 = {producer, MMA, encode x 2}
+constexpr int T2_PRODUCER_WARP = 16, T2_MMA_WARP = 17, T2_ENC_WARP0 = 18, T2_ENC_WARPS = 2;
+constexpr int T2_THREADS = 32 * (T2_ENC_WARP0 + T2_ENC_WARPS);   // 640: 96 registers per thread at launch
+// setmaxnreg moves registers inside the pool the CTA was LAUNCHED with (640 threads x 96), not the whole register file
+constexpr int T2_REGS_EPI = 104, T2_REGS_CTRL = 64;               // 512 x 104 + 128 x 64 = 61 440 = 640 x 96
+constexpr int T2_ENC_ROWS = TM / (32 * T2_ENC_WARPS);             // rows of a tile each encode thread handles (2)
 constexpr int T2_NF = 27;                     // raw features per sample: 24 trilinear channels, x, y, z
 constexpr float kLeaky = 0.01f;
 
@@ -148,6 +148,31 @@ __device__ __forceinline__ void math_dir(const uint32_t* v, const float* rcbias,
   }
 }
 
+// A non-dir layer half is 128 wide: 32 accumulator columns per thread, consumed in two batches of 16 (16 live registers
+// instead of 32); after the last load the accumulator is handed back.  Returns the partial sigma dot product.
+__device__ __forceinline__ float epi_batches(int epi, uint32_t acc_addr, const float* bias, const float* rcbias,
+                                             const float* sigw, uint32_t bar_free, int lane, uint32_t (&out)[16]) {
+  float part = 0.0f;
+#pragma unroll
+  for (int bt = 0; bt < 2; ++bt) {
+    uint32_t v[16];
+    tmem_ld16(acc_addr + 16 * bt, v);
+    tmem_ld_wait();
+    if (bt == 1) {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_free);
+    }
+    switch (epi) {
+      case EPI_HIDDEN: math_hidden<16, true, false>(v, bias + 16 * bt, out + 8 * bt); break;
+      case EPI_HIDDEN_RC: math_hidden<16, true, true>(v, rcbias + 16 * bt, out + 8 * bt); break;
+      case EPI_FINAL: math_hidden<16, false, false>(v, bias + 16 * bt, out + 8 * bt); break;
+      default: part += math_hidden_sigma<16>(v, bias + 16 * bt, sigw + 16 * bt, out + 8 * bt); break;   // EPI_HIDDEN_SIGMA
+    }
+  }
+  return part;
+}
+
 // shared-memory carve-up (byte offsets from the 1024-byte aligned base)
 constexpr uint32_t OFF_X = 0;
 constexpr uint32_t OFF_B = OFF_X + 6 * ATOM_BYTES;                    // weight ring
@@ -229,27 +254,11 @@ __device__ __forceinline__ void epi_event(const EpiShared& S, int T, int A, int 
     asm volatile("bar.sync 1, %0;" ::"n"(T2_EPI_THREADS) : "memory");  // scratch reusable
     return;
   }
-  // every non-dir layer half is 128 wide: 32 columns per thread, in two batches of 16
   float part = 0.0f;
-  auto run = [&](uint32_t (&out)[16]) {
-#pragma unroll
-    for (int bt = 0; bt < 2; ++bt) {
-      uint32_t v[16];
-      tmem_ld16(acc_addr + 16 * bt, v);
-      tmem_ld_wait();
-      if (bt == 1) release_acc();
-      switch (Ly.epi) {
-        case EPI_HIDDEN: math_hidden<16, true, false>(v, bias + 16 * bt, out + 8 * bt); break;
-        case EPI_HIDDEN_RC: math_hidden<16, true, true>(v, rc + Ly.rc_base + n + 16 * bt, out + 8 * bt); break;
-        case EPI_FINAL: math_hidden<16, false, false>(v, bias + 16 * bt, out + 8 * bt); break;
-        default:   // EPI_HIDDEN_SIGMA
-          part += math_hidden_sigma<16>(v, bias + 16 * bt, Pf + (Ly.branch ? p.L.osigma_w : p.L.sigma_w) + n + 16 * bt, out + 8 * bt);
-          break;
-      }
-    }
-  };
   if (Ly.nhalf == 2 && h == 0) {
-    run(stash);                                  // kept in registers until the MMAs of half 1 have read the old activations
+    // kept in registers until the MMAs of half 1 have read the old activations
+    part = epi_batches(Ly.epi, acc_addr, bias, rc + Ly.rc_base + n, Pf + (Ly.branch ? p.L.osigma_w : p.L.sigma_w) + n,
+                       bar_acc_free + 8 * A, S.lane, stash);
     if (Ly.epi == EPI_HIDDEN_SIGMA) sigma_part = part;
     return;
   }
@@ -257,7 +266,8 @@ __device__ __forceinline__ void epi_event(const EpiShared& S, int T, int A, int 
   // in place, half 0 first (its registers are free before this half's outputs are formed)
   if (Ly.nhalf == 2) tmem_st16(h_addr + (uint32_t)(S.cq * 16), stash);
   uint32_t pk[16];
-  run(pk);
+  part = epi_batches(Ly.epi, acc_addr, bias, rc + Ly.rc_base + n, Pf + (Ly.branch ? p.L.osigma_w : p.L.sigma_w) + n,
+                     bar_acc_free + 8 * A, S.lane, pk);
   if (Ly.epi == EPI_HIDDEN_SIGMA) sigma_part = (Ly.nhalf == 2) ? sigma_part + part : part;
   tmem_st16(h_addr + (uint32_t)((Ly.nhalf == 2 ? 64 : 0) + S.cq * 16), pk);
   tmem_st_wait();
@@ -355,8 +365,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) field_tc2_kernel(const __grid_c
   const int64_t n_pairs = (n_tiles + 1) / 2;
   const uint8_t* blob = reinterpret_cast<const uint8_t*>(p.packed);
 
-  if (warp >= 16 && warp < T2_ENC_WARP0) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(T2_REGS_CTRL));
-  else if (warp >= T2_ENC_WARP0) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(T2_REGS_ENC));
+  if (warp >= 16) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(T2_REGS_CTRL));
   else asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(T2_REGS_EPI));
 
   if (warp == T2_PRODUCER_WARP) {
@@ -459,10 +468,14 @@ __global__ void __launch_bounds__(T2_THREADS, 1) field_tc2_kernel(const __grid_c
     }
   } else if (warp >= T2_ENC_WARP0) {
     // =============================== encode warps: raw features and XS ===============================
-    const int row = (warp - T2_ENC_WARP0) * 32 + lane;
+    const int row0 = (warp - T2_ENC_WARP0) * 32 + lane;     // this thread's rows: row0 + 64 k
     const GridView g = load_grid_view(p.grid);
     auto gather = [&](int t, int64_t tile, int parity) {
-      gather_tile(p, g, feat + (size_t)t * T2_NF * 128 + row, mute_tab + (parity * 2 + t) * 128 + row, tile * TM + row, total);
+#pragma unroll 1
+      for (int k = 0; k < T2_ENC_ROWS; ++k) {
+        const int row = row0 + 32 * T2_ENC_WARPS * k;
+        gather_tile(p, g, feat + (size_t)t * T2_NF * 128 + row, mute_tab + (parity * 2 + t) * 128 + row, tile * TM + row, total);
+      }
     };
     uint32_t regen = 0;   // regenerations of XS so far (the r-th one waits for the release of the (r-1)-th)
     // The loop starts one (virtual) pair early: a virtual pair has no X to produce, it only prefetches the first real pair.
@@ -477,6 +490,9 @@ __global__ void __launch_bounds__(T2_THREADS, 1) field_tc2_kernel(const __grid_c
             T2_STAMP(threadIdx.x == T2_ENC_WARP0 * 32, 512 + (u * 2 + t) * 4 + 0);
             if (regen > 0) mbar_wait(bar_xs_free, (regen - 1) & 1);   // every MMA that read the previous X has completed
             T2_STAMP(threadIdx.x == T2_ENC_WARP0 * 32, 512 + (u * 2 + t) * 4 + 1);
+#pragma unroll 1
+            for (int k = 0; k < T2_ENC_ROWS; ++k) {
+            const int row = row0 + 32 * T2_ENC_WARPS * k;
             const float* F = feat + (size_t)t * T2_NF * 128 + row;
             float f[8];
 #pragma unroll
@@ -491,6 +507,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) field_tc2_kernel(const __grid_c
               for (int c = 0; c < 8; ++c) f[c] = F[(16 + c) * 128];
               pe8_to_chunks(sX, row, 34, 1, f);       // object voxel block starts at column 272 = chunk 34
               st_chunk(a_chunk_addr(sX, row, 47), 0u, 0u, 0u, 0u);  // columns 376..383
+            }
             }
             fence_async_smem();
             __syncwarp();
