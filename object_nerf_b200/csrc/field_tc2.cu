@@ -79,7 +79,12 @@ struct T2Params {
   int n_xuse;                       // X-fed layers per tile, in program order
   int xuse_full[T2_MAX_XUSE];       // 1: the layer reads all 384 columns (object branch), 0: the first 288 (scene)
   long long* timeline;              // -DONERF_TIMELINE: clock64() stamps of block 0, second tile pair (tools/timeline2.py)
+  // what the epilogue of slot i needs, precomputed (one 16-byte constant-bank load per event instead of address arithmetic):
+  //   x: accumulator column | activation column << 16      y: byte offset of the bias row in shared memory
+  //   z: ray_const / head-weight column offset (floats)     w: SlotEpi flags | accumulator index << 16 | layer N << 20
+  uint4 epi_tab[T2_MAX_SLOTS];
 };
+enum SlotEpi { SE_KIND = 7, SE_TWO = 8, SE_H1 = 16, SE_TILE = 32, SE_BRANCH = 64, SE_N64 = 128 };
 
 #ifdef ONERF_TIMELINE
 #define T2_STAMP(cond, idx) do { if ((cond) && P.timeline && blockIdx.x == 0 && pair == (int64_t)gridDim.x) P.timeline[idx] = clock64(); } while (0)
@@ -177,109 +182,114 @@ __device__ __forceinline__ float epi_batches(int epi, uint32_t acc_addr, const f
 constexpr uint32_t OFF_X = 0;
 constexpr uint32_t OFF_B = OFF_X + 6 * ATOM_BYTES;                    // weight ring
 constexpr uint32_t OFF_F = OFF_B + T2_NSTAGE * T2_STAGE_BYTES;        // [2][27][128] floats: raw features of both tiles
-constexpr uint32_t OFF_MUTE = OFF_F + 2 * T2_NF * 128 * 4;            // [2 parities][2 tiles][128] bytes
-constexpr uint32_t OFF_BIAS = OFF_MUTE + 512;                         // [MAX_LAYERS][256] floats
+constexpr uint32_t OFF_META = OFF_F + 2 * T2_NF * 128 * 4;            // [2 parities][2 tiles][128] int2: ray, sample | flags
+constexpr uint32_t OFF_BIAS = OFF_META + 2 * 2 * 128 * 8;             // [MAX_LAYERS][256] floats
 constexpr uint32_t OFF_SCRATCH = OFF_BIAS + T2_MAX_LAYERS * 256 * 4;  // [128][4][4] floats
 constexpr uint32_t OFF_BAR = OFF_SCRATCH + TM * 4 * 4 * 4;
 constexpr uint32_t T2_SMEM_BYTES = OFF_BAR + 256 + 1024;
 
-struct EpiShared {   // what the epilogue code needs besides the per-event arguments
-  const T2Params* P;
-  uint8_t* smem;             // generic pointer to the aligned shared-memory base
-  uint32_t sbase;            // its shared-window address
-  uint32_t lane_taddr;       // TMEM address of this warp's lane quarter, column 0
-  int row, cq, lane;
-};
-struct TileMeta {            // per tile of the current pair
-  int ray, si;
-  bool live;
-};
-
-// One epilogue event: layer `l`, half `h` of tile `T`, accumulator `A`.  `stash`: the packed outputs of half 0 of a two-half
-// layer (the slots of a tile's layer are consecutive: one stash serves both tiles).
-__device__ __forceinline__ void epi_event(const EpiShared& S, int T, int A, int l, int h, const TileMeta& M, int parity,
-                                          uint32_t (&stash)[16], uint32_t& acc_bits, float& sigma_part) {
-  const T2Params& P = *S.P;
-  const T2Layer& Ly = P.layers[l];
+// One epilogue event (slot `si` of the pair's program).  Live state across events: the 16-register stash, two partial
+// sigma sums and the barrier phase bits; everything else comes from the slot table (constant bank) and the per-row
+// metadata the encode warps left in shared memory.
+__device__ __forceinline__ void epi_event(const T2Params& P, int si, uint8_t* smem, uint32_t sbase, uint32_t lane_taddr,
+                                          int parity, uint32_t (&stash)[16], uint32_t& acc_bits, float& sigma_a, float& sigma_b) {
   const FieldParams& p = P.f;
+  const uint4 e = P.epi_tab[si];
+  const int flags = (int)(e.w & 0xffffu), A = (int)((e.w >> 16) & 15u), N = (int)(e.w >> 20);
+  const int kind = flags & SE_KIND, T = (flags & SE_TILE) ? 1 : 0, branch = (flags & SE_BRANCH) ? 1 : 0;
+  const int lane = threadIdx.x & 31, cq = threadIdx.x >> 7, row = threadIdx.x & 127;
+  const int ncol = (flags & SE_N64) ? 16 : 32;            // accumulator columns of this thread
+  const uint32_t acc_addr = lane_taddr + (e.x & 0xffffu) + (uint32_t)(cq * ncol);
+  const uint32_t h_addr = lane_taddr + (e.x >> 16);
+  const uint32_t bar_acc_ready = sbase + OFF_BAR + 16 * T2_NSTAGE, bar_acc_free = bar_acc_ready + 16, bar_h_ready = bar_acc_free + 16;
   const float* Pf = reinterpret_cast<const float*>(p.packed);
-  const float* bias_tab = reinterpret_cast<const float*>(S.smem + OFF_BIAS);
-  float* scratch = reinterpret_cast<float*>(S.smem + OFF_SCRATCH);
-  const uint32_t bar_acc_ready = S.sbase + OFF_BAR + 16 * T2_NSTAGE, bar_acc_free = bar_acc_ready + 16, bar_h_ready = bar_acc_free + 16;
-  const int HW = Ly.N >> (Ly.nhalf - 1);       // 128, or 64 for the object dir layer
-  const int n = h * HW + S.cq * (HW >> 2);     // first output column of this thread
-  const uint32_t acc_addr = S.lane_taddr + (uint32_t)(A * 128 + S.cq * (HW >> 2));
-  const uint32_t h_addr = S.lane_taddr + (uint32_t)(256 + T * 128);
-  const float* rc = p.ray_const + (int64_t)M.ray * ONERF_RAY_CONST_FLOATS;
+  const int2 meta = *reinterpret_cast<const int2*>(smem + OFF_META + ((parity * 2 + T) * 128 + row) * 8);
+  const float* rc = p.ray_const + (int64_t)meta.x * ONERF_RAY_CONST_FLOATS + e.z + cq * ncol;   // per-ray constants of this thread's columns
   mbar_wait(bar_acc_ready + 8 * A, (acc_bits >> A) & 1u);
   acc_bits ^= 1u << A;
   tc_fence_after();
-  // the accumulator is consumed in batches of 16 columns (16 live registers instead of 32); after the last load it is
-  // handed back: the tile's next MMAs may overwrite it
-  auto release_acc = [&]() {
-    tc_fence_before();
-    __syncwarp();
-    if (S.lane == 0) mbar_arrive(bar_acc_free + 8 * A);
-  };
-  const int nbatch = HW >> 6;                  // 2 (32 columns per thread) or 1 (the 64-wide object dir layer)
-  const float* bias = bias_tab + l * 256 + n;
-  if (Ly.epi == EPI_DIR) {
-    const float* headw = Pf + (Ly.branch ? p.L.orgb_w : p.L.rgb_w) + n;
+  uint32_t v[32];
+  tmem_ld16(acc_addr, v);
+  if (ncol == 32) tmem_ld16(acc_addr + 16, v + 16);
+  tmem_ld_wait();
+  // the accumulator is in registers: the next MMAs may overwrite it
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(bar_acc_free + 8 * A);
+  if (kind == EPI_DIR) {
+    const float* headw = Pf + (branch ? p.L.orgb_w : p.L.rgb_w) + cq * ncol;
     float part0 = 0.0f, part1 = 0.0f, part2 = 0.0f;
-    for (int bt = 0; bt < nbatch; ++bt) {
-      uint32_t v[16];
-      tmem_ld16(acc_addr + 16 * bt, v);
-      tmem_ld_wait();
-      if (bt == nbatch - 1) release_acc();
-      math_dir<16>(v, rc + Ly.rc_base + n + 16 * bt, headw + 16 * bt, Ly.N, part0, part1, part2);
-    }
+    if (ncol == 32) math_dir<32>(v, rc, headw, N, part0, part1, part2);
+    else math_dir<16>(v, rc, headw, N, part0, part1, part2);
     // combine the four column quarters of this row through shared memory, finish the heads, write out
-    float* sc = scratch + (S.row * 4 + S.cq) * 4;
-    sc[0] = sigma_part; sc[1] = part0; sc[2] = part1; sc[3] = part2;
+    float* scratch = reinterpret_cast<float*>(smem + OFF_SCRATCH);
+    float* sc = scratch + (row * 4 + cq) * 4;
+    sc[0] = T ? sigma_b : sigma_a; sc[1] = part0; sc[2] = part1; sc[3] = part2;
     asm volatile("bar.sync 1, %0;" ::"n"(T2_EPI_THREADS) : "memory");
-    if (S.cq == 0 && M.live) {
-      const float4 a1 = *reinterpret_cast<const float4*>(scratch + (S.row * 4 + 1) * 4);
-      const float4 a2 = *reinterpret_cast<const float4*>(scratch + (S.row * 4 + 2) * 4);
-      const float4 a3 = *reinterpret_cast<const float4*>(scratch + (S.row * 4 + 3) * 4);
-      const float* hb = Pf + (Ly.branch ? p.L.orgb_b : p.L.rgb_b);
-      float sg = sigma_part + a1.x + a2.x + a3.x + __ldg(Pf + (Ly.branch ? p.L.osigma_b : p.L.sigma_b));
-      const float r = 1.0f / (1.0f + __expf(-(part0 + a1.y + a2.y + a3.y + __ldg(hb + 0))));
-      const float gch = 1.0f / (1.0f + __expf(-(part1 + a1.z + a2.z + a3.z + __ldg(hb + 1))));
-      const float b = 1.0f / (1.0f + __expf(-(part2 + a1.w + a2.w + a3.w + __ldg(hb + 2))));
-      const int mute = S.smem[OFF_MUTE + (parity * 2 + T) * 128 + S.row];
-      if (mute & (Ly.branch ? 2 : 1)) sg = -1e5f;
-      float* outp = Ly.branch ? p.obj_out : p.scene_out;
-      reinterpret_cast<float4*>(outp)[(int64_t)M.ray * p.out_stride + M.si] = make_float4(r, gch, b, sg);
+    if (cq == 0 && (meta.y & (1 << 30))) {
+      const float4 a0 = *reinterpret_cast<const float4*>(scratch + (row * 4 + 0) * 4);
+      const float4 a1 = *reinterpret_cast<const float4*>(scratch + (row * 4 + 1) * 4);
+      const float4 a2 = *reinterpret_cast<const float4*>(scratch + (row * 4 + 2) * 4);
+      const float4 a3 = *reinterpret_cast<const float4*>(scratch + (row * 4 + 3) * 4);
+      const float* hb = Pf + (branch ? p.L.orgb_b : p.L.rgb_b);
+      float sg = a0.x + a1.x + a2.x + a3.x + __ldg(Pf + (branch ? p.L.osigma_b : p.L.sigma_b));
+      const float r = 1.0f / (1.0f + __expf(-(a0.y + a1.y + a2.y + a3.y + __ldg(hb + 0))));
+      const float gch = 1.0f / (1.0f + __expf(-(a0.z + a1.z + a2.z + a3.z + __ldg(hb + 1))));
+      const float b = 1.0f / (1.0f + __expf(-(a0.w + a1.w + a2.w + a3.w + __ldg(hb + 2))));
+      if ((meta.y >> 28) & (branch ? 2 : 1)) sg = -1e5f;
+      float* outp = branch ? p.obj_out : p.scene_out;
+      reinterpret_cast<float4*>(outp)[(int64_t)meta.x * p.out_stride + (meta.y & 0x0fffffff)] = make_float4(r, gch, b, sg);
     }
     asm volatile("bar.sync 1, %0;" ::"n"(T2_EPI_THREADS) : "memory");  // scratch reusable
     return;
   }
-  float part = 0.0f;
-  if (Ly.nhalf == 2 && h == 0) {
-    // kept in registers until the MMAs of half 1 have read the old activations
-    part = epi_batches(Ly.epi, acc_addr, bias, rc + Ly.rc_base + n, Pf + (Ly.branch ? p.L.osigma_w : p.L.sigma_w) + n,
-                       bar_acc_free + 8 * A, S.lane, stash);
-    if (Ly.epi == EPI_HIDDEN_SIGMA) sigma_part = part;
+  // hidden / final layers: 32 columns per thread
+  const float* bias = reinterpret_cast<const float*>(smem + e.y) + cq * 32;
+  if ((flags & SE_TWO) && !(flags & SE_H1)) {
+    // half 0 of a two-half layer: the outputs wait in registers until the MMAs of half 1 have read the old activations
+    float part = 0.0f;
+    switch (kind) {
+      case EPI_HIDDEN: math_hidden<32, true, false>(v, bias, stash); break;
+      case EPI_HIDDEN_RC: math_hidden<32, true, true>(v, rc, stash); break;
+      case EPI_FINAL: math_hidden<32, false, false>(v, bias, stash); break;
+      default: part = math_hidden_sigma<32>(v, bias, Pf + (branch ? p.L.osigma_w : p.L.sigma_w) + cq * 32, stash); break;
+    }
+    if (kind == EPI_HIDDEN_SIGMA) { if (T) sigma_b = part; else sigma_a = part; }
     return;
   }
-  // this half's accumulator is complete, so every MMA of the layer has finished reading the old activations: overwrite them
-  // in place, half 0 first (its registers are free before this half's outputs are formed)
-  if (Ly.nhalf == 2) tmem_st16(h_addr + (uint32_t)(S.cq * 16), stash);
+  // this half's accumulator was complete, so every MMA of the layer has finished reading the old activations: overwrite
+  // them in place, half 0 first (its registers are free before this half's outputs are formed)
+  uint32_t out_col = (uint32_t)(cq * 16);
+  if (flags & SE_TWO) {
+    tmem_st16(h_addr + out_col, stash);
+    out_col += 64;
+  }
   uint32_t pk[16];
-  part = epi_batches(Ly.epi, acc_addr, bias, rc + Ly.rc_base + n, Pf + (Ly.branch ? p.L.osigma_w : p.L.sigma_w) + n,
-                     bar_acc_free + 8 * A, S.lane, pk);
-  if (Ly.epi == EPI_HIDDEN_SIGMA) sigma_part = (Ly.nhalf == 2) ? sigma_part + part : part;
-  tmem_st16(h_addr + (uint32_t)((Ly.nhalf == 2 ? 64 : 0) + S.cq * 16), pk);
+  float part = 0.0f;
+  switch (kind) {
+    case EPI_HIDDEN: math_hidden<32, true, false>(v, bias, pk); break;
+    case EPI_HIDDEN_RC: math_hidden<32, true, true>(v, rc, pk); break;
+    case EPI_FINAL: math_hidden<32, false, false>(v, bias, pk); break;
+    default:
+      part = math_hidden_sigma<32>(v, bias, Pf + (branch ? p.L.osigma_w : p.L.sigma_w) + ((flags & SE_TWO) ? 128 : 0) + cq * 32, pk);
+      break;
+  }
+  if (kind == EPI_HIDDEN_SIGMA) {
+    if (flags & SE_TWO) part += T ? sigma_b : sigma_a;
+    if (T) sigma_b = part; else sigma_a = part;
+  }
+  tmem_st16(h_addr + out_col, pk);
   tmem_st_wait();
   tc_fence_before();
   __syncwarp();
-  if (S.lane == 0) mbar_arrive(bar_h_ready + 8 * T);
+  if (lane == 0) mbar_arrive(bar_h_ready + 8 * T);
 }
 
 // Trilinear gather of one row's 27 raw features (24 voxel channels, x, y, z) and its mute flags.  Off the critical path: it
 // prefetches the NEXT tile pair.  Inlined at ONE call site: a separately compiled function would not know the register
 // budget setmaxnreg left to the encode warps.
-__device__ __forceinline__ void gather_tile(const FieldParams& p, const GridView& g, float* F, uint8_t* mute_out, int64_t e,
+// meta_out: {ray, sample index | live << 30 | mute bits << 28} for the epilogue's output stage.
+__device__ __forceinline__ void gather_tile(const FieldParams& p, const GridView& g, float* F, int2* meta_out, int64_t e,
                                          int64_t total) {
   const bool live = e < total;
   const int ray = live ? (int)(e / p.S) : 0;
@@ -297,7 +307,7 @@ __device__ __forceinline__ void gather_tile(const FieldParams& p, const GridView
   int mute = 0;  // bit 0: scene sigma muted, bit 1: object sigma muted
   if (live && p.mute_zero_rays && __ldg(p.z + (int64_t)ray * p.z_stride + (p.S - 1)) == 0.0f) mute = 3;
   if (live && mute == 0 && p.n_boxes > 0 && point_in_boxes(p.boxes, p.n_boxes, x, y, z)) mute = 1;
-  *mute_out = (uint8_t)mute;
+  *meta_out = make_int2(ray, si | (live ? (1 << 30) : 0) | (mute << 28));
   float f[8];
   voxel_trilinear<0, 8, false>(g, x, y, z, f);
 #pragma unroll
@@ -327,7 +337,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) field_tc2_kernel(const __grid_c
   const uint32_t tmem_slot = bar_xs_free + 8;
   uint8_t* gen_base = smem_raw + (sbase - smem_u32(smem_raw));
   float* feat = reinterpret_cast<float*>(gen_base + OFF_F);
-  uint8_t* mute_tab = gen_base + OFF_MUTE;
+  int2* meta_tab = reinterpret_cast<int2*>(gen_base + OFF_META);
   float* bias_tab = reinterpret_cast<float*>(gen_base + OFF_BIAS);
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - sbase));
   const float* Pf = reinterpret_cast<const float*>(p.packed);
@@ -397,6 +407,9 @@ __global__ void __launch_bounds__(T2_THREADS, 1) field_tc2_kernel(const __grid_c
     // =============================== MMA issuer ===============================
     uint32_t stage = 0, phase = 0, xs_phase = 0;
     uint32_t free_bits = 0, h_bits = 0;   // per-tile barrier phases, bit t
+#ifdef ONERF_TIMELINE
+    long long wsum = 0;
+#endif
     for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
       for (int si = 0; si < P.n_slots; ++si) {
         const T2Slot sl = P.slots[si];
@@ -427,8 +440,16 @@ __global__ void __launch_bounds__(T2_THREADS, 1) field_tc2_kernel(const __grid_c
             mbar_wait(bar_xs_ready, xs_phase);
             xs_phase ^= 1;
           }
+#ifdef ONERF_TIMELINE
+          const long long tw0 = clock64();
+#endif
           mbar_wait(bar_full + 8 * stage, phase);
           tc_fence_after();
+#ifdef ONERF_TIMELINE
+          if (gi == 0) wsum = 0;
+          wsum += clock64() - tw0;
+          if (lane == 0 && gi == Ly.ngroups - 1 && P.timeline && blockIdx.x == 0 && pair == (int64_t)gridDim.x) P.timeline[si * 8 + 3] = wsum;
+#endif
           T2_STAMP(lane == 0 && gi == 0, si * 8 + 1);
           if (elect_one()) {
             uint32_t accum = accum0;
@@ -474,7 +495,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) field_tc2_kernel(const __grid_c
 #pragma unroll 1
       for (int k = 0; k < T2_ENC_ROWS; ++k) {
         const int row = row0 + 32 * T2_ENC_WARPS * k;
-        gather_tile(p, g, feat + (size_t)t * T2_NF * 128 + row, mute_tab + (parity * 2 + t) * 128 + row, tile * TM + row, total);
+        gather_tile(p, g, feat + (size_t)t * T2_NF * 128 + row, meta_tab + (parity * 2 + t) * 128 + row, tile * TM + row, total);
       }
     };
     uint32_t regen = 0;   // regenerations of XS so far (the r-th one waits for the release of the (r-1)-th)
@@ -522,11 +543,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) field_tc2_kernel(const __grid_c
     }
   } else if (warp < 16) {
     // =============================== epilogue warps ===============================
-    EpiShared S;
-    S.P = &P; S.smem = gen_base; S.sbase = sbase;
-    const int q = warp & 3;
-    S.cq = warp >> 2; S.lane = lane; S.row = q * 32 + lane;
-    S.lane_taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t lane_taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     uint32_t acc_bits = 0;
     uint32_t stash[16];
     float sigma_a = 0.0f, sigma_b = 0.0f;
@@ -535,26 +552,12 @@ __global__ void __launch_bounds__(T2_THREADS, 1) field_tc2_kernel(const __grid_c
       mbar_arrive(bar_acc_free);
       mbar_arrive(bar_acc_free + 8);
     }
-    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-      const int parity = (int)(((pair - blockIdx.x) / gridDim.x) & 1);
-      TileMeta M[2];
-#pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        const int64_t e = (2 * pair + t) * TM + S.row;
-        M[t].live = e < total;
-        M[t].ray = M[t].live ? (int)(e / p.S) : 0;
-        M[t].si = M[t].live ? (int)(e - (int64_t)M[t].ray * p.S) : 0;
-      }
+    int parity = 0;
+    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, parity ^= 1) {
 #pragma unroll 1
       for (int si = 0; si < P.n_slots; ++si) {
-        const T2Slot sl = P.slots[si];
-        const int T = sl.tile;
         T2_STAMP(threadIdx.x == 0, si * 8 + 4);
-        TileMeta Mt;
-        Mt.ray = T ? M[1].ray : M[0].ray; Mt.si = T ? M[1].si : M[0].si; Mt.live = T ? M[1].live : M[0].live;
-        float sg = T ? sigma_b : sigma_a;
-        epi_event(S, T, sl.flags >> 4, sl.layer, sl.half, Mt, parity, stash, acc_bits, sg);
-        if (T) sigma_b = sg; else sigma_a = sg;
+        epi_event(P, si, gen_base, sbase, lane_taddr, parity, stash, acc_bits, sigma_a, sigma_b);
         T2_STAMP(threadIdx.x == 0, si * 8 + 5);
       }
     }
@@ -642,6 +645,17 @@ int onerf_launch_field_bf16_two_tile(onerf_ctx* ctx, const FieldParams& fp, cuda
   }
   P.n_slots = ns;
   P.n_xuse = nx;
+  for (int i = 0; i < ns; ++i) {
+    const T2Slot& sl = P.slots[i];
+    const T2Layer& t = P.layers[sl.layer];
+    const int acc = sl.flags >> 4, HW = t.N >> (t.nhalf - 1);
+    uint32_t flags = (uint32_t)t.epi | (t.nhalf == 2 ? SE_TWO : 0) | (sl.half ? SE_H1 : 0) | (sl.tile ? SE_TILE : 0) |
+                     (t.branch ? SE_BRANCH : 0) | (HW == 64 ? SE_N64 : 0);
+    P.epi_tab[i].x = (uint32_t)(acc * 128) | ((uint32_t)(256 + sl.tile * 128) << 16);
+    P.epi_tab[i].y = OFF_BIAS + (uint32_t)(sl.layer * 256 + sl.half * 128) * 4u;
+    P.epi_tab[i].z = (uint32_t)(t.rc_base + sl.half * 128);
+    P.epi_tab[i].w = flags | ((uint32_t)acc << 16) | ((uint32_t)t.N << 20);
+  }
   const int64_t total = (int64_t)fp.n_rays * fp.S;
   const int64_t tiles = (total + TM - 1) / TM, pairs = (tiles + 1) / 2;
   const int blocks = (int)(pairs < ctx->num_sms ? pairs : ctx->num_sms);
