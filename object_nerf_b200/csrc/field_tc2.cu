@@ -203,11 +203,13 @@ __device__ __forceinline__ void epi_event(const T2Params& P, int si, uint8_t* sm
   const uint32_t h_addr = lane_taddr + (e.x >> 16);
   const uint32_t bar_acc_ready = sbase + OFF_BAR + 16 * T2_NSTAGE, bar_acc_free = bar_acc_ready + 16, bar_h_ready = bar_acc_free + 16;
   const float* Pf = reinterpret_cast<const float*>(p.packed);
-  const int2 meta = *reinterpret_cast<const int2*>(smem + OFF_META + ((parity * 2 + T) * 128 + row) * 8);
-  const float* rc = p.ray_const + (int64_t)meta.x * ONERF_RAY_CONST_FLOATS + e.z + cq * ncol;   // per-ray constants of this thread's columns
   mbar_wait(bar_acc_ready + 8 * A, (acc_bits >> A) & 1u);
   acc_bits ^= 1u << A;
   tc_fence_after();
+  // per-row metadata of this pair, written by the encode warps before the pair's first X was produced (read it only
+  // after an accumulator of the pair is ready: that orders it after the gather)
+  const int2 meta = *reinterpret_cast<const int2*>(smem + OFF_META + ((parity * 2 + T) * 128 + row) * 8);
+  const float* rc = p.ray_const + (int64_t)meta.x * ONERF_RAY_CONST_FLOATS + e.z + cq * ncol;   // per-ray constants of this thread's columns
   uint32_t v[32];
   tmem_ld16(acc_addr, v);
   if (ncol == 32) tmem_ld16(acc_addr + 16, v + 16);
