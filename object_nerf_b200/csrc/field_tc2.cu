@@ -38,8 +38,8 @@ using namespace tc;
 
 constexpr int T2_NSTAGE = 3;
 constexpr int T2_SLAB_BYTES = 8192;          // 128 rows x 64 B: one K-slab (32 of K) of one N = 128 half
-constexpr int T2_STAGE_SLABS = 3;
-constexpr int T2_STAGE_BYTES = T2_STAGE_SLABS * T2_SLAB_BYTES;   // 24 KB
+constexpr int T2_STAGE_SLABS = 4;            // every ring stage costs the issuing warp ~500 cycles of waits / commit /
+constexpr int T2_STAGE_BYTES = T2_STAGE_SLABS * T2_SLAB_BYTES;   // reconvergence whatever it holds: 8 MMAs per 32 KB stage
 constexpr int T2_MAX_GROUPS = 8;
 constexpr int T2_MAX_LAYERS = 16;
 constexpr int T2_MAX_SLOTS = 56;
@@ -80,7 +80,7 @@ struct T2Params {
   int xuse_full[T2_MAX_XUSE];       // 1: the layer reads all 384 columns (object branch), 0: the first 288 (scene)
   long long* timeline;              // -DONERF_TIMELINE: clock64() stamps of block 0, second tile pair (tools/timeline2.py)
   // what the epilogue of slot i needs, precomputed (one 16-byte constant-bank load per event instead of address arithmetic):
-  //   x: accumulator column | activation column << 16      y: byte offset of the bias row in shared memory
+  //   x: accumulator column | activation column << 16      y: float offset of the bias row in the packed blob
   //   z: ray_const / head-weight column offset (floats)     w: SlotEpi flags | accumulator index << 16 | layer N << 20
   uint4 epi_tab[T2_MAX_SLOTS];
 };
@@ -108,8 +108,7 @@ __device__ __forceinline__ void math_hidden(const uint32_t* v, const float* bias
 #pragma unroll
   for (int j4 = 0; j4 < NC / 4; ++j4) {
     float4 b;
-    if (BIAS_GLOBAL) b = __ldg(reinterpret_cast<const float4*>(bias) + j4);
-    else b = *(reinterpret_cast<const float4*>(bias) + j4);
+    b = __ldg(reinterpret_cast<const float4*>(bias) + j4);
     uint32_t p0 = pack_bf16(__uint_as_float(v[4 * j4 + 0]) + b.x, __uint_as_float(v[4 * j4 + 1]) + b.y);
     uint32_t p1 = pack_bf16(__uint_as_float(v[4 * j4 + 2]) + b.z, __uint_as_float(v[4 * j4 + 3]) + b.w);
     if (ACT) { p0 = leaky_bf16x2(p0); p1 = leaky_bf16x2(p1); }
@@ -123,7 +122,7 @@ __device__ __forceinline__ float math_hidden_sigma(const uint32_t* v, const floa
   float part = 0.0f;
 #pragma unroll
   for (int j4 = 0; j4 < NC / 4; ++j4) {
-    const float4 b = *(reinterpret_cast<const float4*>(bias) + j4);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + j4);
     const float4 w = __ldg(reinterpret_cast<const float4*>(headw) + j4);
     float t0 = __uint_as_float(v[4 * j4 + 0]) + b.x, t1 = __uint_as_float(v[4 * j4 + 1]) + b.y;
     float t2 = __uint_as_float(v[4 * j4 + 2]) + b.z, t3 = __uint_as_float(v[4 * j4 + 3]) + b.w;
@@ -183,9 +182,8 @@ constexpr uint32_t OFF_X = 0;
 constexpr uint32_t OFF_B = OFF_X + 6 * ATOM_BYTES;                    // weight ring
 constexpr uint32_t OFF_F = OFF_B + T2_NSTAGE * T2_STAGE_BYTES;        // [2][27][128] floats: raw features of both tiles
 constexpr uint32_t OFF_META = OFF_F + 2 * T2_NF * 128 * 4;            // [2 parities][2 tiles][128] int2: ray, sample | flags
-constexpr uint32_t OFF_BIAS = OFF_META + 2 * 2 * 128 * 8;             // [MAX_LAYERS][256] floats
-constexpr uint32_t OFF_SCRATCH = OFF_BIAS + T2_MAX_LAYERS * 256 * 4;  // [128][4][4] floats
-constexpr uint32_t OFF_BAR = OFF_SCRATCH + TM * 4 * 4 * 4;
+constexpr uint32_t OFF_SCRATCH = OFF_META + 2 * 2 * 128 * 8;          // [4][128] floats (head partial sums, one quantity at a time)
+constexpr uint32_t OFF_BAR = OFF_SCRATCH + 4 * 128 * 4;
 constexpr uint32_t T2_SMEM_BYTES = OFF_BAR + 256 + 1024;
 
 // One epilogue event (slot `si` of the pair's program).  Live state across events: the 16-register stash, two partial
@@ -223,30 +221,32 @@ __device__ __forceinline__ void epi_event(const T2Params& P, int si, uint8_t* sm
     float part0 = 0.0f, part1 = 0.0f, part2 = 0.0f;
     if (ncol == 32) math_dir<32>(v, rc, headw, N, part0, part1, part2);
     else math_dir<16>(v, rc, headw, N, part0, part1, part2);
-    // combine the four column quarters of this row through shared memory, finish the heads, write out
+    // combine the four column quarters of this row through shared memory (one quantity per round: the scratch is 2 KB),
+    // finish the heads, write out
     float* scratch = reinterpret_cast<float*>(smem + OFF_SCRATCH);
-    float* sc = scratch + (row * 4 + cq) * 4;
-    sc[0] = T ? sigma_b : sigma_a; sc[1] = part0; sc[2] = part1; sc[3] = part2;
-    asm volatile("bar.sync 1, %0;" ::"n"(T2_EPI_THREADS) : "memory");
+    float tot[4];
+    const float mine[4] = {T ? sigma_b : sigma_a, part0, part1, part2};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      scratch[cq * 128 + row] = mine[k];
+      asm volatile("bar.sync 1, %0;" ::"n"(T2_EPI_THREADS) : "memory");
+      tot[k] = scratch[row] + scratch[128 + row] + scratch[256 + row] + scratch[384 + row];
+      asm volatile("bar.sync 1, %0;" ::"n"(T2_EPI_THREADS) : "memory");
+    }
     if (cq == 0 && (meta.y & (1 << 30))) {
-      const float4 a0 = *reinterpret_cast<const float4*>(scratch + (row * 4 + 0) * 4);
-      const float4 a1 = *reinterpret_cast<const float4*>(scratch + (row * 4 + 1) * 4);
-      const float4 a2 = *reinterpret_cast<const float4*>(scratch + (row * 4 + 2) * 4);
-      const float4 a3 = *reinterpret_cast<const float4*>(scratch + (row * 4 + 3) * 4);
       const float* hb = Pf + (branch ? p.L.orgb_b : p.L.rgb_b);
-      float sg = a0.x + a1.x + a2.x + a3.x + __ldg(Pf + (branch ? p.L.osigma_b : p.L.sigma_b));
-      const float r = 1.0f / (1.0f + __expf(-(a0.y + a1.y + a2.y + a3.y + __ldg(hb + 0))));
-      const float gch = 1.0f / (1.0f + __expf(-(a0.z + a1.z + a2.z + a3.z + __ldg(hb + 1))));
-      const float b = 1.0f / (1.0f + __expf(-(a0.w + a1.w + a2.w + a3.w + __ldg(hb + 2))));
+      float sg = tot[0] + __ldg(Pf + (branch ? p.L.osigma_b : p.L.sigma_b));
+      const float r = 1.0f / (1.0f + __expf(-(tot[1] + __ldg(hb + 0))));
+      const float gch = 1.0f / (1.0f + __expf(-(tot[2] + __ldg(hb + 1))));
+      const float b = 1.0f / (1.0f + __expf(-(tot[3] + __ldg(hb + 2))));
       if ((meta.y >> 28) & (branch ? 2 : 1)) sg = -1e5f;
       float* outp = branch ? p.obj_out : p.scene_out;
       reinterpret_cast<float4*>(outp)[(int64_t)meta.x * p.out_stride + (meta.y & 0x0fffffff)] = make_float4(r, gch, b, sg);
     }
-    asm volatile("bar.sync 1, %0;" ::"n"(T2_EPI_THREADS) : "memory");  // scratch reusable
     return;
   }
-  // hidden / final layers: 32 columns per thread
-  const float* bias = reinterpret_cast<const float*>(smem + e.y) + cq * 32;
+  // hidden / final layers: 32 columns per thread; biases come straight from the packed blob (14 KB per model: L1 hits)
+  const float* bias = Pf + (int64_t)e.y + cq * 32;
   if ((flags & SE_TWO) && !(flags & SE_H1)) {
     // half 0 of a two-half layer: the outputs wait in registers until the MMAs of half 1 have read the old activations
     float part = 0.0f;
@@ -340,7 +340,6 @@ __global__ void __launch_bounds__(T2_THREADS, 1) field_tc2_kernel(const __grid_c
   uint8_t* gen_base = smem_raw + (sbase - smem_u32(smem_raw));
   float* feat = reinterpret_cast<float*>(gen_base + OFF_F);
   int2* meta_tab = reinterpret_cast<int2*>(gen_base + OFF_META);
-  float* bias_tab = reinterpret_cast<float*>(gen_base + OFF_BIAS);
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - sbase));
   const float* Pf = reinterpret_cast<const float*>(p.packed);
 
@@ -359,10 +358,6 @@ __global__ void __launch_bounds__(T2_THREADS, 1) field_tc2_kernel(const __grid_c
     fence_barrier_init();
   }
   if (warp == T2_MMA_WARP) tmem_alloc(tmem_slot, 512);
-  for (int i = threadIdx.x; i < P.n_layers * 256; i += T2_THREADS) {
-    const int l = i >> 8, c = i & 255;
-    bias_tab[i] = (c < P.layers[l].N) ? __ldg(Pf + P.layers[l].bias_off + c) : 0.0f;
-  }
   // XS starts as zeros: columns a layer's weights do not reach (scene layers: 272..287, pads) must stay finite
   for (uint32_t i = threadIdx.x; i < 6u * ATOM_BYTES / 16u; i += T2_THREADS)
     asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(sX + i * 16u), "r"(0u) : "memory");
@@ -436,8 +431,19 @@ __global__ void __launch_bounds__(T2_THREADS, 1) field_tc2_kernel(const __grid_c
           const int grp = Ly.groups[gi];
           const int first = grp & 31, cnt = (grp >> 5) & 7;
           const bool from_h = (grp >> 8) & 1;
+          // Operand words are formed BEFORE the barrier waits (the empty asm pins them there): whatever sits between a
+          // satisfied wait and the tcgen05.mma instructions is pure latency on the slot-to-slot dependency chain.
           const uint32_t b_lo0 = (((sB + stage * T2_STAGE_BYTES) >> 4) & 0x3FFFu) | 0x10000u;
+          uint32_t a_w[T2_STAGE_SLABS], b_w[T2_STAGE_SLABS];
+#pragma unroll
+          for (int i2 = 0; i2 < T2_STAGE_SLABS; ++i2) {
+            const int sl_i = first + i2;          // X slab: atom sl_i / 2, 64-byte half sl_i % 2;  H slab: 16 TMEM columns
+            a_w[i2] = from_h ? h_tmem + (uint32_t)sl_i * 16u
+                             : ((((sX + (uint32_t)(sl_i >> 1) * ATOM_BYTES) >> 4) & 0x3FFFu) | 0x10000u) + (uint32_t)(sl_i & 1) * 4u;
+            b_w[i2] = b_lo0 + (uint32_t)i2 * hb16;
+          }
           const uint32_t accum0 = (gi > 0) ? 1u : 0u;
+          asm volatile("" ::"r"(a_w[0]), "r"(a_w[1]), "r"(a_w[2]), "r"(a_w[3]), "r"(b_w[0]), "r"(b_w[1]), "r"(b_w[2]), "r"(b_w[3]), "r"(accum0), "r"(d_tmem), "r"(idesc));
           if (gi == 0 && (sl.flags & SLOT_WAIT_XS)) {   // XS holds this tile's X
             mbar_wait(bar_xs_ready, xs_phase);
             xs_phase ^= 1;
@@ -459,11 +465,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1) field_tc2_kernel(const __grid_c
 #pragma unroll
               for (int i2 = 0; i2 < T2_STAGE_SLABS; ++i2) {
                 if (i2 < cnt) {
-                  const int s = first + i2;     // X slab: atom s / 2, 64-byte half s % 2
-                  const uint32_t a_lo = ((((sX + (uint32_t)(s >> 1) * ATOM_BYTES) >> 4) & 0x3FFFu) | 0x10000u) + (uint32_t)(s & 1) * 4u;
-                  const uint32_t b_lo = b_lo0 + (uint32_t)i2 * hb16;
-                  umma_bf16(d_tmem, make_desc_hl(a_lo, DESC_HI_SW128), make_desc_hl(b_lo, DESC_HI_SW64), idesc, accum);
-                  umma_bf16(d_tmem, make_desc_hl(a_lo + 2u, DESC_HI_SW128), make_desc_hl(b_lo + 2u, DESC_HI_SW64), idesc, 1u);
+                  umma_bf16(d_tmem, make_desc_hl(a_w[i2], DESC_HI_SW128), make_desc_hl(b_w[i2], DESC_HI_SW64), idesc, accum);
+                  umma_bf16(d_tmem, make_desc_hl(a_w[i2] + 2u, DESC_HI_SW128), make_desc_hl(b_w[i2] + 2u, DESC_HI_SW64), idesc, 1u);
                   accum = 1u;
                 }
               }
@@ -471,10 +474,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1) field_tc2_kernel(const __grid_c
 #pragma unroll
               for (int i2 = 0; i2 < T2_STAGE_SLABS; ++i2) {
                 if (i2 < cnt) {
-                  const uint32_t b_lo = b_lo0 + (uint32_t)i2 * hb16;
-                  const uint32_t a0 = h_tmem + (uint32_t)(first + i2) * 16u;
-                  umma_bf16_ts(d_tmem, a0, make_desc_hl(b_lo, DESC_HI_SW64), idesc, accum);
-                  umma_bf16_ts(d_tmem, a0 + 8u, make_desc_hl(b_lo + 2u, DESC_HI_SW64), idesc, 1u);
+                  umma_bf16_ts(d_tmem, a_w[i2], make_desc_hl(b_w[i2], DESC_HI_SW64), idesc, accum);
+                  umma_bf16_ts(d_tmem, a_w[i2] + 8u, make_desc_hl(b_w[i2] + 2u, DESC_HI_SW64), idesc, 1u);
                   accum = 1u;
                 }
               }
@@ -654,7 +655,7 @@ int onerf_launch_field_bf16_two_tile(onerf_ctx* ctx, const FieldParams& fp, cuda
     uint32_t flags = (uint32_t)t.epi | (t.nhalf == 2 ? SE_TWO : 0) | (sl.half ? SE_H1 : 0) | (sl.tile ? SE_TILE : 0) |
                      (t.branch ? SE_BRANCH : 0) | (HW == 64 ? SE_N64 : 0);
     P.epi_tab[i].x = (uint32_t)(acc * 128) | ((uint32_t)(256 + sl.tile * 128) << 16);
-    P.epi_tab[i].y = OFF_BIAS + (uint32_t)(sl.layer * 256 + sl.half * 128) * 4u;
+    P.epi_tab[i].y = (uint32_t)(t.bias_off + sl.half * 128);
     P.epi_tab[i].z = (uint32_t)(t.rc_base + sl.half * 128);
     P.epi_tab[i].w = flags | ((uint32_t)acc << 16) | ((uint32_t)t.N << 20);
   }

@@ -23,7 +23,7 @@ lib.onerf_debug_timeline2(buf.data_ptr())
 engine.field(rays, z, packed, grid, codes=codes, precision="bf16")
 torch.cuda.synchronize()
 t = buf.cpu().tolist()
-t0 = min(v for v in t if v > 0)
+t0 = min(v for v in t if v > 10**9)
 names = ["S0", "S1", "S2", "S3", "S4", "S5", "S6", "S7", "FIN", "DIR", "O0", "O1", "O2", "O3", "OFIN", "ODIR"]
 # slot order: per layer: two-half -> (A,0)(A,1)(B,0)(B,1); one-half -> (A)(B)
 slots = []
