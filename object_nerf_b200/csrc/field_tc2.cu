@@ -65,7 +65,12 @@ struct T2Layer {
   int writes_h;     // the epilogue leaves activations for the next layer (everything except the dir layers)
   int64_t img_off, bias_off;
   int ngroups, n_xgroups;
-  int groups[T2_MAX_GROUPS];   // bits [0,5) first slab (inside X or H), [5,8) slab count (1..3), bit 8: from H
+  int groups[T2_MAX_GROUPS];   // bits [0,5) first slab (inside X or H), [5,8) slab count (1..4), bit 8: from H
+  // what the MMA warp adds to the operand base for slab i of group g (formed on the host: the issuing warp shares its
+  // scheduler with four epilogue warps, every instruction it does not execute shortens the slot):
+  //   X slab s: (s / 2) * (ATOM_BYTES / 16) + (s % 2) * 4   (16-byte units, added to the XS descriptor word)
+  //   H slab s: 16 s                                         (TMEM columns, added to the tile's activation base)
+  uint32_t a_rel[T2_MAX_GROUPS][T2_STAGE_SLABS];
 };
 struct T2Slot {
   uint8_t tile, layer, half, flags;   // flags: SlotFlags | accumulator index << 4
@@ -204,6 +209,9 @@ __device__ __forceinline__ void epi_event(const T2Params& P, int si, uint8_t* sm
   mbar_wait(bar_acc_ready + 8 * A, (acc_bits >> A) & 1u);
   acc_bits ^= 1u << A;
   tc_fence_after();
+#ifdef ONERF_TIMELINE
+  if (threadIdx.x == 0 && P.timeline && blockIdx.x == 0 && parity == 1) P.timeline[si * 8 + 6] = clock64();
+#endif
   // per-row metadata of this pair, written by the encode warps before the pair's first X was produced (read it only
   // after an accumulator of the pair is ready: that orders it after the gather)
   const int2 meta = *reinterpret_cast<const int2*>(smem + OFF_META + ((parity * 2 + T) * 128 + row) * 8);
@@ -404,6 +412,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) field_tc2_kernel(const __grid_c
     // =============================== MMA issuer ===============================
     uint32_t stage = 0, phase = 0, xs_phase = 0;
     uint32_t free_bits = 0, h_bits = 0;   // per-tile barrier phases, bit t
+    const uint32_t ring16 = ((sB >> 4) & 0x3FFFu) | 0x10000u, xs16 = ((sX >> 4) & 0x3FFFu) | 0x10000u;   // descriptor low words
 #ifdef ONERF_TIMELINE
     long long wsum = 0;
 #endif
@@ -429,17 +438,16 @@ __global__ void __launch_bounds__(T2_THREADS, 1) field_tc2_kernel(const __grid_c
         tc_fence_after();
         for (int gi = 0; gi < Ly.ngroups; ++gi) {
           const int grp = Ly.groups[gi];
-          const int first = grp & 31, cnt = (grp >> 5) & 7;
+          const int cnt = (grp >> 5) & 7;
           const bool from_h = (grp >> 8) & 1;
           // Operand words are formed BEFORE the barrier waits (the empty asm pins them there): whatever sits between a
           // satisfied wait and the tcgen05.mma instructions is pure latency on the slot-to-slot dependency chain.
-          const uint32_t b_lo0 = (((sB + stage * T2_STAGE_BYTES) >> 4) & 0x3FFFu) | 0x10000u;
+          const uint32_t b_lo0 = ring16 + stage * (T2_STAGE_BYTES >> 4);
+          const uint32_t a_base = from_h ? h_tmem : xs16;
           uint32_t a_w[T2_STAGE_SLABS], b_w[T2_STAGE_SLABS];
 #pragma unroll
           for (int i2 = 0; i2 < T2_STAGE_SLABS; ++i2) {
-            const int sl_i = first + i2;          // X slab: atom sl_i / 2, 64-byte half sl_i % 2;  H slab: 16 TMEM columns
-            a_w[i2] = from_h ? h_tmem + (uint32_t)sl_i * 16u
-                             : ((((sX + (uint32_t)(sl_i >> 1) * ATOM_BYTES) >> 4) & 0x3FFFu) | 0x10000u) + (uint32_t)(sl_i & 1) * 4u;
+            a_w[i2] = a_base + Ly.a_rel[gi][i2];
             b_w[i2] = b_lo0 + (uint32_t)i2 * hb16;
           }
           const uint32_t accum0 = (gi > 0) ? 1u : 0u;
@@ -450,6 +458,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) field_tc2_kernel(const __grid_c
           }
 #ifdef ONERF_TIMELINE
           const long long tw0 = clock64();
+          T2_STAMP(lane == 0 && si == 4, 600 + gi * 4 + 0);
 #endif
           mbar_wait(bar_full + 8 * stage, phase);
           tc_fence_after();
@@ -459,6 +468,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) field_tc2_kernel(const __grid_c
           if (lane == 0 && gi == Ly.ngroups - 1 && P.timeline && blockIdx.x == 0 && pair == (int64_t)gridDim.x) P.timeline[si * 8 + 3] = wsum;
 #endif
           T2_STAMP(lane == 0 && gi == 0, si * 8 + 1);
+          T2_STAMP(lane == 0 && si == 4, 600 + gi * 4 + 1);
           if (elect_one()) {
             uint32_t accum = accum0;
             if (!from_h) {
@@ -480,11 +490,13 @@ __global__ void __launch_bounds__(T2_THREADS, 1) field_tc2_kernel(const __grid_c
                 }
               }
             }
+            T2_STAMP(si == 4, 600 + gi * 4 + 2);
             umma_commit(bar_empty + 8 * stage);
             if (gi == Ly.n_xgroups - 1 && (sl.flags & SLOT_XS_RELEASE)) umma_commit(bar_xs_free);
             if (gi == Ly.ngroups - 1) umma_commit(bar_acc_ready + 8 * acc);
           }
           __syncwarp();
+          T2_STAMP(lane == 0 && si == 4, 600 + gi * 4 + 3);
           T2_STAMP(lane == 0 && gi == Ly.ngroups - 1, si * 8 + 2);
           if (++stage == T2_NSTAGE) { stage = 0; phase ^= 1; }
         }
@@ -602,6 +614,11 @@ int onerf_launch_field_bf16_two_tile(onerf_ctx* ctx, const FieldParams& fp, cuda
     t.n_xgroups = ng;
     emit(nh, 1);
     t.ngroups = ng;
+    for (int g = 0; g < ng; ++g)
+      for (int i2 = 0; i2 < T2_STAGE_SLABS; ++i2) {
+        const int s = (t.groups[g] & 31) + i2;
+        t.a_rel[g][i2] = ((t.groups[g] >> 8) & 1) ? (uint32_t)s * 16u : (uint32_t)(s >> 1) * (ATOM_BYTES >> 4) + (uint32_t)(s & 1) * 4u;
+      }
   };
   if (fp.want_scene) {
     add(G_S0, xs, 0, EPI_HIDDEN, 0, 0);

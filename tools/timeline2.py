@@ -32,10 +32,13 @@ for l, nm in enumerate(names):
     for tile in "AB":
         for h in ((0, 1) if two else (0,)):
             slots.append(f"{tile}.{nm}.h{h}")
-print(f"{'slot':12s} {'mma_top':>8s} {'waits':>8s} {'issued':>8s} {'w_full':>7s} | {'epi_start':>9s} {'epi_end':>8s} {'epi_len':>7s}  (cycles)")
+print(f"{'slot':12s} {'mma_top':>8s} {'waits':>8s} {'issued':>8s} {'w_full':>7s} | {'epi_start':>9s} {'acc_rdy':>8s} {'epi_end':>8s} {'work':>6s}  (cycles)")
 for si, nm in enumerate(slots):
-    r = [t[si * 8 + k] - t0 if t[si * 8 + k] > 0 else -1 for k in (0, 1, 2, 4, 5)]
-    print(f"{nm:12s} {r[0]:8d} {r[1]:8d} {r[2]:8d} {t[si * 8 + 3]:7d} | {r[3]:9d} {r[4]:8d} {r[4] - r[3]:7d}")
+    r = [t[si * 8 + k] - t0 if t[si * 8 + k] > 0 else -1 for k in (0, 1, 2, 4, 6, 5)]
+    print(f"{nm:12s} {r[0]:8d} {r[1]:8d} {r[2]:8d} {t[si * 8 + 3]:7d} | {r[3]:9d} {r[4]:8d} {r[5]:8d} {r[5] - r[4]:6d}")
+print("slot 4 (A.S1.h0) per ring stage: before full wait, after wait, MMAs issued, after commit + syncwarp")
+for gi in range(3):
+    print("  stage", gi, [t[600 + gi * 4 + k] - t0 if t[600 + gi * 4 + k] > 0 else -1 for k in range(4)])
 print("XS regenerations (before wait, after wait, done):")
 for i in range(8):
     r = [t[512 + i * 4 + k] - t0 if t[512 + i * 4 + k] > 0 else -1 for k in range(3)]
