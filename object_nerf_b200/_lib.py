@@ -13,7 +13,7 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libonerf_sm100.so")
+LIB_PATH = os.environ.get("ONERF_LIB_PATH") or os.path.join(_HERE, "libonerf_sm100.so")   # override: A/B experiments
 CSRC = os.path.join(_HERE, "csrc")
 
 PREC_FP32, PREC_BF16 = 0, 1

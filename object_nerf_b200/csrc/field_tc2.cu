@@ -1,11 +1,11 @@
 // Two-tile tcgen05 implementation of the fused encode + two-branch MLP for sm_100a (voxel model, inference).
 //
 // The one-tile kernel (field_tc.cu) leaves the tensor pipe idle two thirds of the time: one 128-row tile has a single
-// dependency chain  MMA(layer l) -> epilogue(l) -> MMA(l + 1)  and the ~950-cycle epilogues of its 16 warps cannot hide
-// behind its own MMAs (profiles/r01_experiments.md).  Here a CTA owns TWO 128-row tiles (A, B) that walk the layer
-// program in lockstep, half a layer apart: while the 16 epilogue warps drain a layer half of one tile, the tensor pipe
-// runs the same layer half of the other.
+// dependency chain  MMA(layer l) -> epilogue(l) -> MMA(l + 1)  and the epilogues of its warps cannot hide behind its own
+// MMAs (profiles/r01_experiments.md).  Here a CTA owns TWO 128-row tiles (A, B) that walk the layer program together:
+// while the 16 epilogue warps drain a layer half of one tile, the tensor pipe runs a layer half of the other.
 //   slot order per two-half layer l :  (A,l,h0) (A,l,h1) (B,l,h0) (B,l,h1);  one-half layers (N <= 128): (A,l) (B,l)
+//                                      object branch first, then the scene branch (see the launcher)
 //   TMEM (512 columns)              :  two 128-column accumulators SHARED by the tiles (half h of a two-half layer uses
 //                                      accumulator h, a one-half layer of tile t uses accumulator t), so consecutive slots
 //                                      never wait for each other's epilogue; activations of tile t at [256 + 128 t, +128)
@@ -13,14 +13,15 @@
 //                                      the MMAs of half 1 have read the old activations
 //   shared memory                   :  ONE 96 KB buffer XS for the encoded input X (the A operand of the four X-fed layers),
 //                                      regenerated from 27 raw features per sample (24 trilinear voxel channels + xyz,
-//                                      kept in shared memory for both tiles) by two dedicated encode warps each time a
-//                                      tile reaches an X-fed layer; 3 x 24 KB weight ring; biases
-//   warps 0-15  epilogue (both tiles, alternating)    warp 16  weight producer (cp.async.bulk)
-//   warp 17     tcgen05.mma issuer (owns TMEM)        warps 18-19  encode: trilinear gather of the NEXT tile pair,
-//                                                                  positional encoding into XS (two rows per thread)
-// Registers are re-divided between the warpgroups with setmaxnreg (epilogue 104, control / encode 64).
+//                                      kept in shared memory for both tiles) each time a tile reaches an X-fed layer;
+//                                      3 x 32 KB weight ring; per-row metadata; 2 KB head scratch
+//   warps 0-15  epilogue of both tiles, alternating, AND the X productions (events of one program, ev_tab)
+//   warp 16     weight producer (cp.async.bulk)     warp 17  tcgen05.mma issuer (owns TMEM)
+//   warps 18-19 trilinear gather of the NEXT tile pair's raw features
+// Registers are re-divided between the warpgroups with setmaxnreg (epilogue 88, the other four warps 128).
 // mbarriers: full / empty (ring), acc_ready[a] (MMA -> epilogue), acc_free[a] (the epilogue has loaded accumulator a: the
-// next MMAs may overwrite it), h_ready[t] (a layer's activations of tile t are written), xs_ready / xs_free (XS hand-over).
+// next MMAs may overwrite it), h_ready[t] (a layer's activations of tile t are written), xs_ready (XS holds the next X),
+// f_ready[t] / f_free[t] (raw features of tile t: gather warps <-> epilogue warps).
 // Arithmetic is that of the one-tile kernel (same K order, same epilogue math): results are bit-identical to it.
 //
 // Reference semantics: models/rendering.py:85-137, models/nerf_model.py:97-152,
@@ -44,18 +45,23 @@ constexpr int T2_MAX_GROUPS = 8;
 constexpr int T2_MAX_LAYERS = 16;
 constexpr int T2_MAX_SLOTS = 56;
 constexpr int T2_MAX_XUSE = 4;
+constexpr int T2_MAX_EVENTS = T2_MAX_SLOTS + 2 * T2_MAX_XUSE;
 constexpr int T2_EPI_THREADS = 512;
 // warpgroups (setmaxnreg works per group of 4 warps): 0-3 epilogue, 4 = {producer, MMA, encode x 2}
 constexpr int T2_PRODUCER_WARP = 16, T2_MMA_WARP = 17, T2_ENC_WARP0 = 18, T2_ENC_WARPS = 2;
 constexpr int T2_THREADS = 32 * (T2_ENC_WARP0 + T2_ENC_WARPS);   // 640: 96 registers per thread at launch
 // setmaxnreg moves registers inside the pool the CTA was LAUNCHED with (640 threads x 96), not the whole register file
-constexpr int T2_REGS_EPI = 104, T2_REGS_CTRL = 64;               // 512 x 104 + 128 x 64 = 61 440 = 640 x 96
+#ifndef T2_REGS_EPI_V
+#define T2_REGS_EPI_V 88
+#define T2_REGS_CTRL_V 128
+#endif
+constexpr int T2_REGS_EPI = T2_REGS_EPI_V, T2_REGS_CTRL = T2_REGS_CTRL_V;   // 512 x EPI + 128 x CTRL = 61 440 = 640 x 96
 constexpr int T2_ENC_ROWS = TM / (32 * T2_ENC_WARPS);             // rows of a tile each encode thread handles (2)
 constexpr int T2_NF = 27;                     // raw features per sample: 24 trilinear channels, x, y, z
 constexpr float kLeaky = 0.01f;
 
-enum Epi { EPI_HIDDEN = 0, EPI_HIDDEN_RC = 1, EPI_HIDDEN_SIGMA = 2, EPI_FINAL = 3, EPI_DIR = 4 };
-enum SlotFlags { SLOT_WAIT_H = 1, SLOT_WAIT_XS = 2, SLOT_XS_RELEASE = 4 };
+enum Epi { EPI_HIDDEN = 0, EPI_HIDDEN_RC = 1, EPI_HIDDEN_SIGMA = 2, EPI_FINAL = 3, EPI_DIR = 4, EV_XGEN = 5 };
+enum SlotFlags { SLOT_WAIT_H = 1, SLOT_WAIT_XS = 2 };
 
 struct T2Layer {
   int N;            // outputs of the layer
@@ -87,14 +93,19 @@ struct T2Params {
   // what the epilogue of slot i needs, precomputed (one 16-byte constant-bank load per event instead of address arithmetic):
   //   x: accumulator column | activation column << 16      y: float offset of the bias row in the packed blob
   //   z: ray_const / head-weight column offset (floats)     w: SlotEpi flags | accumulator index << 16 | layer N << 20
-  uint4 epi_tab[T2_MAX_SLOTS];
+  // An EV_XGEN event (the 16 epilogue warps write a tile's encoded input X into XS) has w = EV_XGEN | XgenFlags << 8 and
+  //   x: accumulator whose completion says that XS is free (the last slot of the other tile's X-fed layer), 0xff: none
+  uint4 ev_tab[T2_MAX_EVENTS];
+  int n_events;
 };
 enum SlotEpi { SE_KIND = 7, SE_TWO = 8, SE_H1 = 16, SE_TILE = 32, SE_BRANCH = 64, SE_N64 = 128 };
+enum XgenFlags { XG_TILE = 1, XG_FULL = 2, XG_WAIT_F = 4, XG_RELEASE_F = 8 };
 
-#ifdef ONERF_TIMELINE
-#define T2_STAMP(cond, idx) do { if ((cond) && P.timeline && blockIdx.x == 0 && pair == (int64_t)gridDim.x) P.timeline[idx] = clock64(); } while (0)
+// -DONERF_WAITSTATS: block 0 accumulates the cycles each role spends in each kind of barrier wait (timeline[900 + k])
+#ifdef ONERF_WAITSTATS
+#define T2_WAIT(k, call) do { const long long w0_ = clock64(); call; wstat[k] += clock64() - w0_; } while (0)
 #else
-#define T2_STAMP(cond, idx) do { } while (0)
+#define T2_WAIT(k, call) do { call; } while (0)
 #endif
 
 // ------------------------------------------------------------------------------------------------
@@ -113,7 +124,11 @@ __device__ __forceinline__ void math_hidden(const uint32_t* v, const float* bias
 #pragma unroll
   for (int j4 = 0; j4 < NC / 4; ++j4) {
     float4 b;
+#ifdef T2_EXP_NO_BIAS
+    b = make_float4(0.f, 0.f, 0.f, 0.f);
+#else
     b = __ldg(reinterpret_cast<const float4*>(bias) + j4);
+#endif
     uint32_t p0 = pack_bf16(__uint_as_float(v[4 * j4 + 0]) + b.x, __uint_as_float(v[4 * j4 + 1]) + b.y);
     uint32_t p1 = pack_bf16(__uint_as_float(v[4 * j4 + 2]) + b.z, __uint_as_float(v[4 * j4 + 3]) + b.w);
     if (ACT) { p0 = leaky_bf16x2(p0); p1 = leaky_bf16x2(p1); }
@@ -194,10 +209,13 @@ constexpr uint32_t T2_SMEM_BYTES = OFF_BAR + 256 + 1024;
 // One epilogue event (slot `si` of the pair's program).  Live state across events: the 16-register stash, two partial
 // sigma sums and the barrier phase bits; everything else comes from the slot table (constant bank) and the per-row
 // metadata the encode warps left in shared memory.
-__device__ __forceinline__ void epi_event(const T2Params& P, int si, uint8_t* smem, uint32_t sbase, uint32_t lane_taddr,
-                                          int parity, uint32_t (&stash)[16], uint32_t& acc_bits, float& sigma_a, float& sigma_b) {
+__device__ __forceinline__ void epi_event(const T2Params& P, const uint4 e, uint8_t* smem, uint32_t sbase, uint32_t lane_taddr,
+                                          int parity, uint32_t (&stash)[16], uint32_t& acc_bits, float& sigma_a, float& sigma_b
+#ifdef ONERF_WAITSTATS
+                                          , long long* wstat
+#endif
+                                          ) {
   const FieldParams& p = P.f;
-  const uint4 e = P.epi_tab[si];
   const int flags = (int)(e.w & 0xffffu), A = (int)((e.w >> 16) & 15u), N = (int)(e.w >> 20);
   const int kind = flags & SE_KIND, T = (flags & SE_TILE) ? 1 : 0, branch = (flags & SE_BRANCH) ? 1 : 0;
   const int lane = threadIdx.x & 31, cq = threadIdx.x >> 7, row = threadIdx.x & 127;
@@ -206,17 +224,17 @@ __device__ __forceinline__ void epi_event(const T2Params& P, int si, uint8_t* sm
   const uint32_t h_addr = lane_taddr + (e.x >> 16);
   const uint32_t bar_acc_ready = sbase + OFF_BAR + 16 * T2_NSTAGE, bar_acc_free = bar_acc_ready + 16, bar_h_ready = bar_acc_free + 16;
   const float* Pf = reinterpret_cast<const float*>(p.packed);
-  mbar_wait(bar_acc_ready + 8 * A, (acc_bits >> A) & 1u);
+  T2_WAIT(6, mbar_wait(bar_acc_ready + 8 * A, (acc_bits >> A) & 1u));
   acc_bits ^= 1u << A;
   tc_fence_after();
-#ifdef ONERF_TIMELINE
-  if (threadIdx.x == 0 && P.timeline && blockIdx.x == 0 && parity == 1) P.timeline[si * 8 + 6] = clock64();
-#endif
   // per-row metadata of this pair, written by the encode warps before the pair's first X was produced (read it only
   // after an accumulator of the pair is ready: that orders it after the gather)
   const int2 meta = *reinterpret_cast<const int2*>(smem + OFF_META + ((parity * 2 + T) * 128 + row) * 8);
   const float* rc = p.ray_const + (int64_t)meta.x * ONERF_RAY_CONST_FLOATS + e.z + cq * ncol;   // per-ray constants of this thread's columns
   uint32_t v[32];
+#ifdef ONERF_WAITSTATS
+  const long long ph0 = clock64();
+#endif
   tmem_ld16(acc_addr, v);
   if (ncol == 32) tmem_ld16(acc_addr + 16, v + 16);
   tmem_ld_wait();
@@ -224,6 +242,11 @@ __device__ __forceinline__ void epi_event(const T2Params& P, int si, uint8_t* sm
   tc_fence_before();
   __syncwarp();
   if (lane == 0) mbar_arrive(bar_acc_free + 8 * A);
+#ifdef ONERF_WAITSTATS
+  const long long ph1 = clock64();
+  wstat[0] += ph1 - ph0;
+  if (kind == EPI_DIR) wstat[4] -= ph1; else if ((flags & SE_TWO) && !(flags & SE_H1)) wstat[1] -= ph1; else wstat[2] -= ph1;
+#endif
   if (kind == EPI_DIR) {
     const float* headw = Pf + (branch ? p.L.orgb_w : p.L.rgb_w) + cq * ncol;
     float part0 = 0.0f, part1 = 0.0f, part2 = 0.0f;
@@ -251,8 +274,21 @@ __device__ __forceinline__ void epi_event(const T2Params& P, int si, uint8_t* sm
       float* outp = branch ? p.obj_out : p.scene_out;
       reinterpret_cast<float4*>(outp)[(int64_t)meta.x * p.out_stride + (meta.y & 0x0fffffff)] = make_float4(r, gch, b, sg);
     }
+#ifdef ONERF_WAITSTATS
+    wstat[4] += clock64();
+#endif
     return;
   }
+#ifdef T2_EXP_NO_EPI
+  if (kind != EPI_DIR) {   // experiment: no epilogue math (garbage results), only the barrier protocol
+    if ((flags & SE_TWO) && !(flags & SE_H1)) return;
+    tmem_st_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_h_ready + 8 * T);
+    return;
+  }
+#endif
   // hidden / final layers: 32 columns per thread; biases come straight from the packed blob (14 KB per model: L1 hits)
   const float* bias = Pf + (int64_t)e.y + cq * 32;
   if ((flags & SE_TWO) && !(flags & SE_H1)) {
@@ -265,6 +301,10 @@ __device__ __forceinline__ void epi_event(const T2Params& P, int si, uint8_t* sm
       default: part = math_hidden_sigma<32>(v, bias, Pf + (branch ? p.L.osigma_w : p.L.sigma_w) + cq * 32, stash); break;
     }
     if (kind == EPI_HIDDEN_SIGMA) { if (T) sigma_b = part; else sigma_a = part; }
+#ifdef ONERF_WAITSTATS
+    asm volatile("" ::"r"(stash[0]), "r"(stash[15]));
+    wstat[1] += clock64();
+#endif
     return;
   }
   // this half's accumulator was complete, so every MMA of the layer has finished reading the old activations: overwrite
@@ -288,16 +328,24 @@ __device__ __forceinline__ void epi_event(const T2Params& P, int si, uint8_t* sm
     if (flags & SE_TWO) part += T ? sigma_b : sigma_a;
     if (T) sigma_b = part; else sigma_a = part;
   }
+#ifdef ONERF_WAITSTATS
+  asm volatile("" ::"r"(pk[0]), "r"(pk[15]));
+  const long long ph2 = clock64();
+  wstat[2] += ph2;
+#endif
   tmem_st16(h_addr + out_col, pk);
   tmem_st_wait();
   tc_fence_before();
   __syncwarp();
   if (lane == 0) mbar_arrive(bar_h_ready + 8 * T);
+#ifdef ONERF_WAITSTATS
+  wstat[3] += clock64() - ph2;
+#endif
 }
 
 // Trilinear gather of one row's 27 raw features (24 voxel channels, x, y, z) and its mute flags.  Off the critical path: it
 // prefetches the NEXT tile pair.  Inlined at ONE call site: a separately compiled function would not know the register
-// budget setmaxnreg left to the encode warps.
+// budget setmaxnreg left to the gather warps.
 // meta_out: {ray, sample index | live << 30 | mute bits << 28} for the epilogue's output stage.
 __device__ __forceinline__ void gather_tile(const FieldParams& p, const GridView& g, float* F, int2* meta_out, int64_t e,
                                          int64_t total) {
@@ -343,8 +391,9 @@ __global__ void __launch_bounds__(T2_THREADS, 1) field_tc2_kernel(const __grid_c
   const uint32_t bar_acc_ready = sBar + 16 * T2_NSTAGE;              // [2]
   const uint32_t bar_acc_free = bar_acc_ready + 16;                  // [2]
   const uint32_t bar_h_ready = bar_acc_free + 16;                    // [2]
-  const uint32_t bar_xs_ready = bar_h_ready + 16, bar_xs_free = bar_xs_ready + 8;
-  const uint32_t tmem_slot = bar_xs_free + 8;
+  const uint32_t bar_xs_ready = bar_h_ready + 16;
+  const uint32_t bar_f_ready = bar_xs_ready + 8, bar_f_free = bar_f_ready + 16;   // [2] each: raw features of tile t
+  const uint32_t tmem_slot = bar_f_free + 16;
   uint8_t* gen_base = smem_raw + (sbase - smem_u32(smem_raw));
   float* feat = reinterpret_cast<float*>(gen_base + OFF_F);
   int2* meta_tab = reinterpret_cast<int2*>(gen_base + OFF_META);
@@ -361,8 +410,11 @@ __global__ void __launch_bounds__(T2_THREADS, 1) field_tc2_kernel(const __grid_c
       mbar_init(bar_acc_free + 8 * t, T2_EPI_THREADS / 32);
       mbar_init(bar_h_ready + 8 * t, T2_EPI_THREADS / 32);
     }
-    mbar_init(bar_xs_ready, T2_ENC_WARPS);
-    mbar_init(bar_xs_free, 1);
+    mbar_init(bar_xs_ready, T2_EPI_THREADS / 32);
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(bar_f_ready + 8 * t, T2_ENC_WARPS);
+      mbar_init(bar_f_free + 8 * t, T2_EPI_THREADS / 32);
+    }
     fence_barrier_init();
   }
   if (warp == T2_MMA_WARP) tmem_alloc(tmem_slot, 512);
@@ -378,186 +430,161 @@ __global__ void __launch_bounds__(T2_THREADS, 1) field_tc2_kernel(const __grid_c
   const int64_t total = (int64_t)p.n_rays * p.S;
   const int64_t n_tiles = (total + TM - 1) / TM;
   const int64_t n_pairs = (n_tiles + 1) / 2;
+#ifdef ONERF_WAITSTATS
+  long long wstat[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const long long t_role0 = clock64();
+#endif
   const uint8_t* blob = reinterpret_cast<const uint8_t*>(p.packed);
 
-  if (warp >= 16) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(T2_REGS_CTRL));
-  else asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(T2_REGS_EPI));
-
-  if (warp == T2_PRODUCER_WARP) {
-    // =============================== weight producer ===============================
-    uint32_t stage = 0, phase = 0;
-    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-      for (int si = 0; si < P.n_slots; ++si) {
-        const T2Slot sl = P.slots[si];
-        const T2Layer& Ly = P.layers[sl.layer];
-        const uint32_t slab_bytes = (uint32_t)Ly.N * 64u, half_bytes = slab_bytes >> (Ly.nhalf - 1);
-        const uint8_t* src = blob + Ly.img_off + (size_t)sl.half * half_bytes;
-        for (int gi = 0; gi < Ly.ngroups; ++gi) {
-          const int grp = Ly.groups[gi];
-          const int first = grp & 31, cnt = (grp >> 5) & 7;
-          const int gslab = ((grp >> 8) & 1) ? Ly.nslab_x + first : first;
-          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-          if (elect_one()) {
-            mbar_expect_tx(bar_full + 8 * stage, (uint32_t)cnt * half_bytes);
-            for (int i2 = 0; i2 < cnt; ++i2)
-              tma_bulk_g2s(sB + stage * T2_STAGE_BYTES + (uint32_t)i2 * half_bytes, src + (size_t)(gslab + i2) * slab_bytes,
-                           half_bytes, bar_full + 8 * stage);
-          }
-          __syncwarp();
-          if (++stage == T2_NSTAGE) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-  } else if (warp == T2_MMA_WARP) {
-    // =============================== MMA issuer ===============================
-    uint32_t stage = 0, phase = 0, xs_phase = 0;
-    uint32_t free_bits = 0, h_bits = 0;   // per-tile barrier phases, bit t
-    const uint32_t ring16 = ((sB >> 4) & 0x3FFFu) | 0x10000u, xs16 = ((sX >> 4) & 0x3FFFu) | 0x10000u;   // descriptor low words
-#ifdef ONERF_TIMELINE
-    long long wsum = 0;
-#endif
-    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-      for (int si = 0; si < P.n_slots; ++si) {
-        const T2Slot sl = P.slots[si];
-        const T2Layer& Ly = P.layers[sl.layer];
-        const int t = sl.tile;
-        const uint32_t idesc = make_idesc(Ly.N >> (Ly.nhalf - 1));
-        const uint32_t half_bytes = ((uint32_t)Ly.N * 64u) >> (Ly.nhalf - 1);
-        const uint32_t hb16 = half_bytes >> 4;
-        const int acc = sl.flags >> 4;
-        T2_STAMP(lane == 0, si * 8 + 0);
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 128);
-        const uint32_t h_tmem = tmem_base + (uint32_t)(256 + t * 128);
-        // the epilogue of the accumulator's previous user has loaded it into registers
-        mbar_wait(bar_acc_free + 8 * acc, (free_bits >> acc) & 1u);
-        free_bits ^= 1u << acc;
-        if (sl.flags & SLOT_WAIT_H) {   // the previous layer's activations are written
-          mbar_wait(bar_h_ready + 8 * t, (h_bits >> t) & 1u);
-          h_bits ^= 1u << t;
-        }
-        tc_fence_after();
-        for (int gi = 0; gi < Ly.ngroups; ++gi) {
-          const int grp = Ly.groups[gi];
-          const int cnt = (grp >> 5) & 7;
-          const bool from_h = (grp >> 8) & 1;
-          // Operand words are formed BEFORE the barrier waits (the empty asm pins them there): whatever sits between a
-          // satisfied wait and the tcgen05.mma instructions is pure latency on the slot-to-slot dependency chain.
-          const uint32_t b_lo0 = ring16 + stage * (T2_STAGE_BYTES >> 4);
-          const uint32_t a_base = from_h ? h_tmem : xs16;
-          uint32_t a_w[T2_STAGE_SLABS], b_w[T2_STAGE_SLABS];
-#pragma unroll
-          for (int i2 = 0; i2 < T2_STAGE_SLABS; ++i2) {
-            a_w[i2] = a_base + Ly.a_rel[gi][i2];
-            b_w[i2] = b_lo0 + (uint32_t)i2 * hb16;
-          }
-          const uint32_t accum0 = (gi > 0) ? 1u : 0u;
-          asm volatile("" ::"r"(a_w[0]), "r"(a_w[1]), "r"(a_w[2]), "r"(a_w[3]), "r"(b_w[0]), "r"(b_w[1]), "r"(b_w[2]), "r"(b_w[3]), "r"(accum0), "r"(d_tmem), "r"(idesc));
-          if (gi == 0 && (sl.flags & SLOT_WAIT_XS)) {   // XS holds this tile's X
-            mbar_wait(bar_xs_ready, xs_phase);
-            xs_phase ^= 1;
-          }
-#ifdef ONERF_TIMELINE
-          const long long tw0 = clock64();
-          T2_STAMP(lane == 0 && si == 4, 600 + gi * 4 + 0);
-#endif
-          mbar_wait(bar_full + 8 * stage, phase);
-          tc_fence_after();
-#ifdef ONERF_TIMELINE
-          if (gi == 0) wsum = 0;
-          wsum += clock64() - tw0;
-          if (lane == 0 && gi == Ly.ngroups - 1 && P.timeline && blockIdx.x == 0 && pair == (int64_t)gridDim.x) P.timeline[si * 8 + 3] = wsum;
-#endif
-          T2_STAMP(lane == 0 && gi == 0, si * 8 + 1);
-          T2_STAMP(lane == 0 && si == 4, 600 + gi * 4 + 1);
-          if (elect_one()) {
-            uint32_t accum = accum0;
-            if (!from_h) {
-#pragma unroll
-              for (int i2 = 0; i2 < T2_STAGE_SLABS; ++i2) {
-                if (i2 < cnt) {
-                  umma_bf16(d_tmem, make_desc_hl(a_w[i2], DESC_HI_SW128), make_desc_hl(b_w[i2], DESC_HI_SW64), idesc, accum);
-                  umma_bf16(d_tmem, make_desc_hl(a_w[i2] + 2u, DESC_HI_SW128), make_desc_hl(b_w[i2] + 2u, DESC_HI_SW64), idesc, 1u);
-                  accum = 1u;
-                }
+  // The register budget ptxas compiles a region with is the one of the setmaxnreg that DOMINATES it: the two
+  // instructions sit at the top of the two role regions (a common "if dec else inc" ahead of the role switch made the whole
+  // kernel compile for the smaller budget: every epilogue loop variable lived in local memory).
+  if (warp >= 16) {
+    if (T2_REGS_CTRL < 96) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(T2_REGS_CTRL));
+    if (T2_REGS_CTRL > 96) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(T2_REGS_CTRL));
+    if (warp == T2_PRODUCER_WARP) {
+      // =============================== weight producer ===============================
+      {
+        uint32_t stage = 0, phase = 0;
+        for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+          for (int si = 0; si < P.n_slots; ++si) {
+            const T2Slot sl = P.slots[si];
+            const T2Layer& Ly = P.layers[sl.layer];
+            const uint32_t slab_bytes = (uint32_t)Ly.N * 64u, half_bytes = slab_bytes >> (Ly.nhalf - 1);
+            const uint8_t* src = blob + Ly.img_off + (size_t)sl.half * half_bytes;
+            for (int gi = 0; gi < Ly.ngroups; ++gi) {
+              const int grp = Ly.groups[gi];
+              const int first = grp & 31, cnt = (grp >> 5) & 7;
+              const int gslab = ((grp >> 8) & 1) ? Ly.nslab_x + first : first;
+              T2_WAIT(0, mbar_wait(bar_empty + 8 * stage, phase ^ 1));
+              if (elect_one()) {   // (the uniform-datapath instructions want a region the compiler KNOWS is one lane wide)
+                mbar_expect_tx(bar_full + 8 * stage, (uint32_t)cnt * half_bytes);
+                for (int i2 = 0; i2 < cnt; ++i2)
+                  tma_bulk_g2s(sB + stage * T2_STAGE_BYTES + (uint32_t)i2 * half_bytes, src + (size_t)(gslab + i2) * slab_bytes,
+                               half_bytes, bar_full + 8 * stage);
               }
-            } else {
-#pragma unroll
-              for (int i2 = 0; i2 < T2_STAGE_SLABS; ++i2) {
-                if (i2 < cnt) {
-                  umma_bf16_ts(d_tmem, a_w[i2], make_desc_hl(b_w[i2], DESC_HI_SW64), idesc, accum);
-                  umma_bf16_ts(d_tmem, a_w[i2] + 8u, make_desc_hl(b_w[i2] + 2u, DESC_HI_SW64), idesc, 1u);
-                  accum = 1u;
-                }
-              }
+              __syncwarp();
+              if (++stage == T2_NSTAGE) { stage = 0; phase ^= 1; }
             }
-            T2_STAMP(si == 4, 600 + gi * 4 + 2);
-            umma_commit(bar_empty + 8 * stage);
-            if (gi == Ly.n_xgroups - 1 && (sl.flags & SLOT_XS_RELEASE)) umma_commit(bar_xs_free);
-            if (gi == Ly.ngroups - 1) umma_commit(bar_acc_ready + 8 * acc);
           }
-          __syncwarp();
-          T2_STAMP(lane == 0 && si == 4, 600 + gi * 4 + 3);
-          T2_STAMP(lane == 0 && gi == Ly.ngroups - 1, si * 8 + 2);
-          if (++stage == T2_NSTAGE) { stage = 0; phase ^= 1; }
         }
       }
-    }
-  } else if (warp >= T2_ENC_WARP0) {
-    // =============================== encode warps: raw features and XS ===============================
-    const int row0 = (warp - T2_ENC_WARP0) * 32 + lane;     // this thread's rows: row0 + 64 k
-    const GridView g = load_grid_view(p.grid);
-    auto gather = [&](int t, int64_t tile, int parity) {
-#pragma unroll 1
-      for (int k = 0; k < T2_ENC_ROWS; ++k) {
-        const int row = row0 + 32 * T2_ENC_WARPS * k;
-        gather_tile(p, g, feat + (size_t)t * T2_NF * 128 + row, meta_tab + (parity * 2 + t) * 128 + row, tile * TM + row, total);
+    } else if (warp == T2_MMA_WARP) {
+      // =============================== MMA issuer ===============================
+      // The warp stays converged for the loop control and the waits; ONE elect.sync region per ring stage holds the
+      // tcgen05.mma and tcgen05.commit instructions (inside a plain "if (lane == 0)" the compiler wraps every uniform-
+      // datapath instruction in its own elect loop).
+      {
+        uint32_t stage = 0, phase = 0, xs_phase = 0;
+        uint32_t free_bits = 0, h_bits = 0;   // per-tile barrier phases, bit t
+        const uint32_t ring16 = ((sB >> 4) & 0x3FFFu) | 0x10000u, xs16 = ((sX >> 4) & 0x3FFFu) | 0x10000u;   // descriptor low words
+        for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+          for (int si = 0; si < P.n_slots; ++si) {
+            const T2Slot sl = P.slots[si];
+            const T2Layer& Ly = P.layers[sl.layer];
+            const int t = sl.tile;
+            const uint32_t idesc = make_idesc(Ly.N >> (Ly.nhalf - 1));
+            const uint32_t half_bytes = ((uint32_t)Ly.N * 64u) >> (Ly.nhalf - 1);
+            const uint32_t hb16 = half_bytes >> 4;
+            const int acc = sl.flags >> 4;
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 128);
+            const uint32_t h_tmem = tmem_base + (uint32_t)(256 + t * 128);
+            // the epilogue of the accumulator's previous user has loaded it into registers
+            T2_WAIT(1, mbar_wait(bar_acc_free + 8 * acc, (free_bits >> acc) & 1u));
+            free_bits ^= 1u << acc;
+            if (sl.flags & SLOT_WAIT_H) {   // the previous layer's activations are written
+              T2_WAIT(2, mbar_wait(bar_h_ready + 8 * t, (h_bits >> t) & 1u));
+              h_bits ^= 1u << t;
+            }
+            tc_fence_after();
+            for (int gi = 0; gi < Ly.ngroups; ++gi) {
+              const int grp = Ly.groups[gi];
+              const int cnt = (grp >> 5) & 7;
+              const bool from_h = (grp >> 8) & 1;
+              // Operand words are formed BEFORE the barrier waits (the empty asm pins them there): whatever sits between a
+              // satisfied wait and the tcgen05.mma instructions is pure latency on the slot-to-slot dependency chain.
+              const uint32_t b_lo0 = ring16 + stage * (T2_STAGE_BYTES >> 4);
+              const uint32_t a_base = from_h ? h_tmem : xs16;
+              uint32_t a_w[T2_STAGE_SLABS], b_w[T2_STAGE_SLABS];
+#pragma unroll
+              for (int i2 = 0; i2 < T2_STAGE_SLABS; ++i2) {
+                a_w[i2] = a_base + Ly.a_rel[gi][i2];
+                b_w[i2] = b_lo0 + (uint32_t)i2 * hb16;
+              }
+              uint32_t accum = (gi > 0) ? 1u : 0u;
+              asm volatile("" ::"r"(a_w[0]), "r"(a_w[1]), "r"(a_w[2]), "r"(a_w[3]), "r"(b_w[0]), "r"(b_w[1]), "r"(b_w[2]), "r"(b_w[3]), "r"(accum), "r"(d_tmem), "r"(idesc));
+              if (gi == 0 && (sl.flags & SLOT_WAIT_XS)) {   // XS holds this tile's X
+                T2_WAIT(3, mbar_wait(bar_xs_ready, xs_phase));
+                xs_phase ^= 1;
+              }
+              T2_WAIT(4, mbar_wait(bar_full + 8 * stage, phase));
+              tc_fence_after();
+#ifdef ONERF_WAITSTATS
+              const long long mi0 = clock64();
+#endif
+              if (elect_one()) {
+#ifndef T2_EXP_NO_MMA
+              if (!from_h) {
+#pragma unroll
+                for (int i2 = 0; i2 < T2_STAGE_SLABS; ++i2) {
+                  if (i2 < cnt) {
+                    umma_bf16(d_tmem, make_desc_hl(a_w[i2], DESC_HI_SW128), make_desc_hl(b_w[i2], DESC_HI_SW64), idesc, accum);
+                    umma_bf16(d_tmem, make_desc_hl(a_w[i2] + 2u, DESC_HI_SW128), make_desc_hl(b_w[i2] + 2u, DESC_HI_SW64), idesc, 1u);
+                    accum = 1u;
+                  }
+                }
+              } else {
+#pragma unroll
+                for (int i2 = 0; i2 < T2_STAGE_SLABS; ++i2) {
+                  if (i2 < cnt) {
+                    umma_bf16_ts(d_tmem, a_w[i2], make_desc_hl(b_w[i2], DESC_HI_SW64), idesc, accum);
+                    umma_bf16_ts(d_tmem, a_w[i2] + 8u, make_desc_hl(b_w[i2] + 2u, DESC_HI_SW64), idesc, 1u);
+                    accum = 1u;
+                  }
+                }
+              }
+#endif
+#ifdef ONERF_WAITSTATS
+              const long long mi1 = clock64();
+              wstat[5] += mi1 - mi0;
+#endif
+              umma_commit(bar_empty + 8 * stage);
+              if (gi == Ly.ngroups - 1) umma_commit(bar_acc_ready + 8 * acc);
+#ifdef ONERF_WAITSTATS
+              wstat[7] += clock64() - mi1;
+#endif
+              }
+              __syncwarp();
+              if (++stage == T2_NSTAGE) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
       }
-    };
-    uint32_t regen = 0;   // regenerations of XS so far (the r-th one waits for the release of the (r-1)-th)
-    // The loop starts one (virtual) pair early: a virtual pair has no X to produce, it only prefetches the first real pair.
-    for (int64_t pair = (int64_t)blockIdx.x - (int64_t)gridDim.x; pair < n_pairs; pair += gridDim.x) {
-      const bool real = pair >= 0;
-      const int nu = real ? P.n_xuse : 1;
-      const int64_t next = pair + gridDim.x;
-      const int next_parity = (int)(((next - blockIdx.x) / gridDim.x) & 1);
-      for (int u = 0; u < nu; ++u) {
+    } else {
+      // =============================== gather warps: raw features of the NEXT tile pair ===============================
+      const int row0 = (warp - T2_ENC_WARP0) * 32 + lane;     // this thread's rows: row0 + 64 k
+      const GridView g = load_grid_view(p.grid);
+      uint32_t it = 0;
+      for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++it) {
+#pragma unroll 1
         for (int t = 0; t < 2; ++t) {
-          if (real) {
-            T2_STAMP(threadIdx.x == T2_ENC_WARP0 * 32, 512 + (u * 2 + t) * 4 + 0);
-            if (regen > 0) mbar_wait(bar_xs_free, (regen - 1) & 1);   // every MMA that read the previous X has completed
-            T2_STAMP(threadIdx.x == T2_ENC_WARP0 * 32, 512 + (u * 2 + t) * 4 + 1);
+          // the epilogue warps have encoded the tile's last X of the previous pair: its features may be overwritten
+          if (it > 0) T2_WAIT(5, mbar_wait(bar_f_free + 8 * t, (it - 1) & 1u));
 #pragma unroll 1
-            for (int k = 0; k < T2_ENC_ROWS; ++k) {
+          for (int k = 0; k < T2_ENC_ROWS; ++k) {
             const int row = row0 + 32 * T2_ENC_WARPS * k;
-            const float* F = feat + (size_t)t * T2_NF * 128 + row;
-            float f[8];
-#pragma unroll
-            for (int c = 0; c < 8; ++c) f[c] = F[c * 128];
-            pe8_to_chunks(sX, row, 0, 2, f);          // scene channels 0-7 : chunks 0, 2, 4, ...
-#pragma unroll
-            for (int c = 0; c < 8; ++c) f[c] = F[(8 + c) * 128];
-            pe8_to_chunks(sX, row, 1, 2, f);          // scene channels 8-15: chunks 1, 3, 5, ...
-            pe_xyz_to_chunks(sX, row, 26, F[24 * 128], F[25 * 128], F[26 * 128]);   // columns 208..271
-            if (P.xuse_full[u]) {
-#pragma unroll
-              for (int c = 0; c < 8; ++c) f[c] = F[(16 + c) * 128];
-              pe8_to_chunks(sX, row, 34, 1, f);       // object voxel block starts at column 272 = chunk 34
-              st_chunk(a_chunk_addr(sX, row, 47), 0u, 0u, 0u, 0u);  // columns 376..383
-            }
-            }
-            fence_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_xs_ready);
-            T2_STAMP(threadIdx.x == T2_ENC_WARP0 * 32, 512 + (u * 2 + t) * 4 + 2);
-            ++regen;
+            gather_tile(p, g, feat + (size_t)t * T2_NF * 128 + row, meta_tab + ((it & 1) * 2 + t) * 128 + row,
+                        (2 * pair + t) * TM + row, total);
           }
-          // this tile's features are no longer needed: fetch the next pair's
-          if (u == nu - 1 && next < n_pairs) gather(t, 2 * next + t, next_parity);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_f_ready + 8 * t);
         }
       }
     }
-  } else if (warp < 16) {
+  } else {
     // =============================== epilogue warps ===============================
+    if (T2_REGS_EPI > 96) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(T2_REGS_EPI));
+    if (T2_REGS_EPI < 96) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(T2_REGS_EPI));
     const uint32_t lane_taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     uint32_t acc_bits = 0;
     uint32_t stash[16];
@@ -570,14 +597,58 @@ __global__ void __launch_bounds__(T2_THREADS, 1) field_tc2_kernel(const __grid_c
     int parity = 0;
     for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, parity ^= 1) {
 #pragma unroll 1
-      for (int si = 0; si < P.n_slots; ++si) {
-        T2_STAMP(threadIdx.x == 0, si * 8 + 4);
-        epi_event(P, si, gen_base, sbase, lane_taddr, parity, stash, acc_bits, sigma_a, sigma_b);
-        T2_STAMP(threadIdx.x == 0, si * 8 + 5);
+      for (int ei = 0; ei < P.n_events; ++ei) {
+        const uint4 e = P.ev_tab[ei];
+        if ((e.w & 0xffu) == EV_XGEN) {
+          // ---- X of one tile into XS: row = thread & 127, the four column quarters of the CTA take one block each ----
+          const int xf = (int)(e.w >> 8), t = xf & XG_TILE;
+#ifdef ONERF_WAITSTATS
+          const long long x0 = clock64();
+#endif
+          if (e.x != 0xffu) mbar_wait(bar_acc_ready + 8 * e.x, (acc_bits >> e.x) & 1u);   // (peek) the MMAs that read XS are done
+          if (xf & XG_WAIT_F) mbar_wait(bar_f_ready + 8 * t, (uint32_t)parity);
+          tc_fence_after();
+#ifndef T2_EXP_NO_XGEN
+          const int row = threadIdx.x & 127, q = threadIdx.x >> 7;
+          const float* F = feat + (size_t)t * T2_NF * 128 + row;
+          if (q == 2) {
+            pe_xyz_to_chunks(sX, row, 26, F[24 * 128], F[25 * 128], F[26 * 128]);   // columns 208..271
+          } else if (q < 2 || (xf & XG_FULL)) {
+            float f[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) f[c] = F[((q == 3 ? 16 : 8 * q) + c) * 128];
+            // scene channels 0-7: chunks 0, 2, 4, ...; 8-15: chunks 1, 3, 5, ...; object voxel block: column 272 = chunk 34
+            pe8_to_chunks(sX, row, q == 3 ? 34 : q, q == 3 ? 1 : 2, f);
+            if (q == 3) st_chunk(a_chunk_addr(sX, row, 47), 0u, 0u, 0u, 0u);  // columns 376..383
+          }
+#endif
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(bar_xs_ready);
+            if (xf & XG_RELEASE_F) mbar_arrive(bar_f_free + 8 * t);
+          }
+#ifdef ONERF_WAITSTATS
+          wstat[5] += clock64() - x0;
+#endif
+          continue;
+        }
+        epi_event(P, e, gen_base, sbase, lane_taddr, parity, stash, acc_bits, sigma_a, sigma_b
+#ifdef ONERF_WAITSTATS
+                  , wstat
+#endif
+        );
       }
     }
   }
 
+#ifdef ONERF_WAITSTATS
+  if (P.timeline && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp >= 16)) {
+    long long* o = P.timeline + 900 + (warp == 0 ? 0 : warp - 15) * 10;
+    for (int k = 0; k < 8; ++k) o[k] = wstat[k];
+    o[8] = clock64() - t_role0;
+  }
+#endif
   // ---- teardown ----
   tc_fence_before();
   __syncthreads();
@@ -620,6 +691,16 @@ int onerf_launch_field_bf16_two_tile(onerf_ctx* ctx, const FieldParams& fp, cuda
         t.a_rel[g][i2] = ((t.groups[g] >> 8) & 1) ? (uint32_t)s * 16u : (uint32_t)(s >> 1) * (ATOM_BYTES >> 4) + (uint32_t)(s & 1) * 4u;
       }
   };
+  // Object branch first: a pair's raw features can only be replaced (by the gather of the NEXT pair, ~27K cycles on two
+  // warps) after the tile's last X-fed layer; with the scene branch last that layer is S4 and ten long slots still follow.
+  if (fp.want_object) {
+    add(G_O0, xo, 0, EPI_HIDDEN_RC, 1, RC_OL0);
+    add(G_O1, 0, 4, EPI_HIDDEN, 1, 0);
+    add(G_O2, xo, 4, EPI_HIDDEN_RC, 1, RC_OL2);
+    add(G_O3, 0, 4, EPI_HIDDEN_SIGMA, 1, 0);
+    add(G_OFIN, 0, 4, EPI_FINAL, 1, 0);
+    add(G_ODIR, 0, 4, EPI_DIR, 1, RC_ODIR);
+  }
   if (fp.want_scene) {
     add(G_S0, xs, 0, EPI_HIDDEN, 0, 0);
     add(G_S1, 0, 8, EPI_HIDDEN, 0, 0);
@@ -632,14 +713,6 @@ int onerf_launch_field_bf16_two_tile(onerf_ctx* ctx, const FieldParams& fp, cuda
     add(G_SFIN, 0, 8, EPI_FINAL, 0, 0);
     add(G_SDIR, 0, 8, EPI_DIR, 0, RC_SDIR);
   }
-  if (fp.want_object) {
-    add(G_O0, xo, 0, EPI_HIDDEN_RC, 1, RC_OL0);
-    add(G_O1, 0, 4, EPI_HIDDEN, 1, 0);
-    add(G_O2, xo, 4, EPI_HIDDEN_RC, 1, RC_OL2);
-    add(G_O3, 0, 4, EPI_HIDDEN_SIGMA, 1, 0);
-    add(G_OFIN, 0, 4, EPI_FINAL, 1, 0);
-    add(G_ODIR, 0, 4, EPI_DIR, 1, RC_ODIR);
-  }
   P.n_layers = n;
   // slots of one tile pair
   int ns = 0, nx = 0;
@@ -648,34 +721,53 @@ int onerf_launch_field_bf16_two_tile(onerf_ctx* ctx, const FieldParams& fp, cuda
     P.slots[ns].flags = (uint8_t)flags;
     ++ns;
   };
-  for (int l = 0; l < n; ++l) {
+  auto layer_slots = [&](int tile, int l) {
     const T2Layer& t = P.layers[l];
     const int wait_h = t.nslab_h > 0 ? SLOT_WAIT_H : 0;
-    const bool xfed = t.nslab_x > 0;
-    if (xfed) P.xuse_full[nx++] = t.branch ? 1 : 0;
+    const int wait_x = t.nslab_x > 0 ? SLOT_WAIT_XS : 0;
     // a tile's slots of a layer are consecutive; an X-fed layer keeps XS for all of them
-    for (int tile = 0; tile < 2; ++tile) {
-      if (t.nhalf == 2) {
-        slot(tile, l, 0, wait_h | (xfed ? SLOT_WAIT_XS : 0) | (0 << 4));
-        slot(tile, l, 1, (xfed ? SLOT_XS_RELEASE : 0) | (1 << 4));
-      } else {
-        slot(tile, l, 0, wait_h | (xfed ? (SLOT_WAIT_XS | SLOT_XS_RELEASE) : 0) | (tile << 4));
-      }
+    if (t.nhalf == 2) {
+      slot(tile, l, 0, wait_h | wait_x | (0 << 4));
+      slot(tile, l, 1, 1 << 4);
+    } else {
+      slot(tile, l, 0, wait_h | wait_x | (tile << 4));
     }
+  };
+  for (int l = 0; l < n; ++l) {
+    if (P.layers[l].nslab_x > 0) P.xuse_full[nx++] = P.layers[l].branch ? 1 : 0;
+    for (int tile = 0; tile < 2; ++tile) layer_slots(tile, l);
   }
   P.n_slots = ns;
   P.n_xuse = nx;
+  // The epilogue's program: one event per slot, in slot order, plus the X productions.  XS is one buffer:
+  //   X of tile A for X-fed layer l  : right after A's last event of layer l - 1 (first event of the pair for layer 0); the
+  //                                    previous reader of XS (tile B, an earlier layer) has long completed
+  //   X of tile B for X-fed layer l  : right before the event of A's LAST slot of layer l, once that slot's accumulator is
+  //                                    complete (every MMA of A's layer l has then read XS); the MMA warp is waiting for it
+  int ne = 0, xi = 0;
+  auto xgen = [&](int tile, int u, uint32_t peek_acc) {
+    const uint32_t xf = (tile ? XG_TILE : 0) | (P.xuse_full[u] ? XG_FULL : 0) | (u == 0 ? XG_WAIT_F : 0) | (u == nx - 1 ? XG_RELEASE_F : 0);
+    P.ev_tab[ne].x = peek_acc; P.ev_tab[ne].y = 0; P.ev_tab[ne].z = 0;
+    P.ev_tab[ne].w = (uint32_t)EV_XGEN | (xf << 8);
+    ++ne;
+  };
+  if (n > 0 && P.layers[0].nslab_x > 0) xgen(0, xi, 0xffu);
   for (int i = 0; i < ns; ++i) {
     const T2Slot& sl = P.slots[i];
     const T2Layer& t = P.layers[sl.layer];
     const int acc = sl.flags >> 4, HW = t.N >> (t.nhalf - 1);
+    const bool last_slot_of_layer = (sl.half == t.nhalf - 1);
+    if (sl.tile == 0 && last_slot_of_layer && t.nslab_x > 0) xgen(1, xi++, (uint32_t)acc);
     uint32_t flags = (uint32_t)t.epi | (t.nhalf == 2 ? SE_TWO : 0) | (sl.half ? SE_H1 : 0) | (sl.tile ? SE_TILE : 0) |
                      (t.branch ? SE_BRANCH : 0) | (HW == 64 ? SE_N64 : 0);
-    P.epi_tab[i].x = (uint32_t)(acc * 128) | ((uint32_t)(256 + sl.tile * 128) << 16);
-    P.epi_tab[i].y = (uint32_t)(t.bias_off + sl.half * 128);
-    P.epi_tab[i].z = (uint32_t)(t.rc_base + sl.half * 128);
-    P.epi_tab[i].w = flags | ((uint32_t)acc << 16) | ((uint32_t)t.N << 20);
+    P.ev_tab[ne].x = (uint32_t)(acc * 128) | ((uint32_t)(256 + sl.tile * 128) << 16);
+    P.ev_tab[ne].y = (uint32_t)(t.bias_off + sl.half * 128);
+    P.ev_tab[ne].z = (uint32_t)(t.rc_base + sl.half * 128);
+    P.ev_tab[ne].w = flags | ((uint32_t)acc << 16) | ((uint32_t)t.N << 20);
+    ++ne;
+    if (sl.tile == 0 && last_slot_of_layer && sl.layer + 1 < n && P.layers[sl.layer + 1].nslab_x > 0) xgen(0, xi, 0xffu);
   }
+  P.n_events = ne;
   const int64_t total = (int64_t)fp.n_rays * fp.S;
   const int64_t tiles = (total + TM - 1) / TM, pairs = (tiles + 1) / 2;
   const int blocks = (int)(pairs < ctx->num_sms ? pairs : ctx->num_sms);
