@@ -26,6 +26,7 @@ import statistics
 import subprocess
 import sys
 import tempfile
+import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -55,13 +56,46 @@ def load_peaks():
 
 
 class ClockSampler:
+    """SM clock and throttle reasons of ONE GPU every 100 ms while the timed region runs.  NVML in-process (the library
+    nvidia-smi prints from): eight `nvidia-smi -lms` children starting inside an 8-rank timed region each enumerate every
+    GPU of the box and stalled the launching threads for tens of milliseconds.  Falls back to an nvidia-smi child."""
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
-        self.index, self.proc, self.tmp = index, None, None
+        self.index, self.proc, self.tmp, self.rows, self.thread, self.h = index, None, None, [], None, None
+        self.stop = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[index]) if visible and visible.split(",")[index].strip().isdigit() else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nv = pynvml
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.h = None
+
+    def _poll(self):
+        nv = self.nv
+        masks = [nv.nvmlClocksThrottleReasonHwSlowdown, nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown, nv.nvmlClocksThrottleReasonSwPowerCap]
+        while True:
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((mhz, [bool(r & m) for m in masks]))
+            except Exception:
+                pass
+            if self.stop.wait(0.1):
+                return
 
     def __enter__(self):
+        if self.h is not None:
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return self
         try:
             self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
@@ -72,6 +106,9 @@ class ClockSampler:
         return self
 
     def __exit__(self, *exc):
+        if self.thread is not None:
+            self.stop.set()
+            self.thread.join(timeout=2)
         if self.proc is not None:
             self.proc.terminate()
             try:
@@ -81,6 +118,14 @@ class ClockSampler:
 
     def summary(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.thread is not None:
+            if self.rows:
+                out["sm_mhz"] = statistics.median(r[0] for r in self.rows)
+                out["sm_max_mhz"] = self.max_mhz
+                out["reasons"] = [n for i, n in enumerate(self.NAMES) if any(r[1][i] for r in self.rows)]
+                out["samples"] = len(self.rows)
+                out["source"] = "nvml"
+            return out
         if self.tmp is None:
             return out
         try:
@@ -91,11 +136,11 @@ class ClockSampler:
             if sm:
                 out["sm_mhz"] = statistics.median(sm)
                 out["sm_max_mhz"] = float(rows[0][1])
-                names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-                for i, n in enumerate(names):
+                for i, n in enumerate(self.NAMES):
                     if any(r[2 + i].strip().lower().startswith("active") for r in rows if len(r) >= 6):
                         out["reasons"].append(n)
                 out["samples"] = len(sm)
+                out["source"] = "nvidia-smi"
         except Exception:
             pass
         return out
@@ -419,8 +464,8 @@ def run_train(args, rank, world, dev, sc, timer, peaks):
         torch.cuda.current_stream().synchronize()
 
     steps = max(args.steps * 4, 20)
-    for _ in range(5):
-        step_device()
+    for _ in range(20):      # DDP rebuilds its buckets after the first step and NCCL connects channels lazily: at 8 ranks
+        step_device()        # the first dozen steps carry one-off stalls of hundreds of milliseconds
     l0 = _lib.launch_count(dev)
     ms = timer.timed(step_device, steps)
     launches = (_lib.launch_count(dev) - l0) / steps
@@ -566,7 +611,6 @@ def run_ours(args, rank, world, local_rank):
         codes_dev = code_lib.lookup(ids_dev)
     rays_host, ids_host = sc["rays"].pin_memory(), sc["ids"].pin_memory()
     out_host = torch.empty(N_RAYS, 4, dtype=torch.float32).pin_memory()
-    tiles = [torch.empty(N_RAYS, 4, device=dev) for _ in range(world)] if world > 1 else None
 
     def render(rays, codes, precision=None, keys=("rgb_fine", "depth_fine")):
         n = rays.shape[0]
@@ -580,11 +624,8 @@ def run_ours(args, rank, world, local_rank):
                 rgbd[i:i + CHUNK, 3] = r[keys[1]]
         return rgbd
 
-    def step_device():
-        rgbd = render(rays_dev, codes_dev)
-        if world > 1:
-            dist.all_gather(tiles, rgbd)
-        return rgbd
+    def step_device():          # weak scaling: every rank renders its own frame, no collective on the data path
+        return render(rays_dev, codes_dev)
 
     def step_e2e():
         r = rays_host.to(dev, non_blocking=True)
@@ -592,15 +633,14 @@ def run_ours(args, rank, world, local_rank):
         with torch.no_grad():
             c = code_lib.lookup(ids)             # the code-library gather runs on the device: 8 B of ids per ray cross PCIe
         rgbd = render(r, c)
-        if world > 1:
-            dist.all_gather(tiles, rgbd)
         out_host.copy_(rgbd, non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
+    cs = ClockSampler(local_rank)       # NVML is initialised here, outside the timed region
     for _ in range(max(args.warmup, 3)):
         step_device()
     launches0 = _lib.launch_count(dev)
-    with ClockSampler(local_rank) as cs:
+    with cs:
         ms = timer.timed(step_device, args.steps)
     launches = _lib.launch_count(dev) - launches0
     clocks = cs.summary()
@@ -661,7 +701,7 @@ def run_ours(args, rank, world, local_rank):
         "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": N_RAYS * (8 * 4 + 8),
                 "d2h_bytes_per_step": N_RAYS * 4 * 4},
         "gpu_launches": launches,
-        "roofline": {"bound": "tensor", "kernel": "field_tc_kernel<voxel> fine pass (65536 rays x 128 samples)",
+        "roofline": {"bound": "tensor", "kernel": "field_tc2_kernel (two-tile, voxel) fine pass (65536 rays x 128 samples)",
                      "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                      "peak_source": f"{peaks_kind} bf16_tflops_sustained (kernel timed inside the step)",
                      "flops_per_launch": flops, "ms_per_launch": fine_ms,
