@@ -578,9 +578,11 @@ def run_edit(args, dev, sc, models, embeddings):
     boxes = {"4": Box(0), "6": Box(1)}
     chunk = 4096
 
+    n_frame = min(N_RAYS, int(os.environ.get("ONERF_EDIT_CHUNKS", "0")) * chunk or N_RAYS)   # (profiling runs: first chunks only)
+
     def frame():
         with torch.no_grad():
-            for i in range(0, N_RAYS, chunk):
+            for i in range(0, n_frame, chunk):
                 render_rays_multi(models, embeddings, lib, [s[i:i + chunk] for s in sets], [0, 4, 4], N_samples=N_SAMPLES,
                                   N_importance=N_IMPORTANCE, chunk=chunk, white_back=False, background_skip_bbox=boxes,
                                   precision=args.precision)
