@@ -51,7 +51,8 @@ def test_sample_pdf_draws_stay_inside_the_bins_and_merge_is_sorted(seed, n, nb, 
        white=st.booleans())
 def test_compositing_weights_form_a_sub_probability_and_maps_are_bounded(seed, n, s, last, white):
     rng = np.random.default_rng(seed)
-    z = torch.from_numpy(np.sort(rng.uniform(0.1, 5.0, size=(n, s)), axis=1).astype(np.float32))
+    # sorted depths at least 0.01 apart: "opaque" below means sigma * delta >> 1, not sigma alone
+    z = torch.from_numpy((np.sort(rng.uniform(0.1, 5.0, size=(n, s)), axis=1) + 0.01 * np.arange(s)).astype(np.float32))
     sigma = torch.from_numpy(rng.normal(0, 20, size=(n, s)).astype(np.float32))
     rgb = torch.from_numpy(rng.uniform(0, 1, size=(n, s, 3)).astype(np.float32))
     _, w = O.alpha_weights(sigma, z, last)
