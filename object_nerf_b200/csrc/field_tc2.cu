@@ -81,8 +81,19 @@ struct T2Layer {
 struct T2Slot {
   uint8_t tile, layer, half, flags;   // flags: SlotFlags | accumulator index << 4
 };
+// Everything the MMA warp needs for one slot in 64 bytes (four independent 16-byte constant-bank loads, fetched one slot
+// ahead): the per-slot walk through slots[] -> layers[] -> groups[] / a_rel[] was a chain of dependent loads in front of
+// every slot.
+//   q[0].x  instruction descriptor          q[0].y  half bytes / 16 | acc << 16 | tile << 17 | wait_h << 18 | wait_xs << 19 | ngroups << 20
+//   q[0].z  4 bits per group: slab count | from_h << 3
+//   q[1..3] 16-bit operand offsets, half-word 4 g + i = slab i of group g (same meaning as T2Layer::a_rel)
+constexpr int T2_REC_GROUPS = 5;
+struct T2Rec {
+  uint4 q[4];
+};
 struct T2Params {
   FieldParams f;
+  T2Rec rec[T2_MAX_SLOTS];
   T2Layer layers[T2_MAX_LAYERS];
   int n_layers;
   T2Slot slots[T2_MAX_SLOTS];
@@ -478,85 +489,89 @@ __global__ void __launch_bounds__(T2_THREADS, 1) field_tc2_kernel(const __grid_c
         uint32_t stage = 0, phase = 0, xs_phase = 0;
         uint32_t free_bits = 0, h_bits = 0;   // per-tile barrier phases, bit t
         const uint32_t ring16 = ((sB >> 4) & 0x3FFFu) | 0x10000u, xs16 = ((sX >> 4) & 0x3FFFu) | 0x10000u;   // descriptor low words
+        T2Rec cur = P.rec[0];
         for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
           for (int si = 0; si < P.n_slots; ++si) {
-            const T2Slot sl = P.slots[si];
-            const T2Layer& Ly = P.layers[sl.layer];
-            const int t = sl.tile;
-            const uint32_t idesc = make_idesc(Ly.N >> (Ly.nhalf - 1));
-            const uint32_t half_bytes = ((uint32_t)Ly.N * 64u) >> (Ly.nhalf - 1);
-            const uint32_t hb16 = half_bytes >> 4;
-            const int acc = sl.flags >> 4;
+            const T2Rec nxt = P.rec[(si + 1 == P.n_slots) ? 0 : si + 1];   // in flight while this slot waits and issues
+            const uint32_t idesc = cur.q[0].x, hdr = cur.q[0].y, gmeta = cur.q[0].z;
+            const uint32_t hb16 = hdr & 0xffffu;
+            const int acc = (hdr >> 16) & 1, t = (hdr >> 17) & 1, ngroups = (int)(hdr >> 20);
+            const uint32_t rel[2 * T2_REC_GROUPS] = {cur.q[1].x, cur.q[1].y, cur.q[1].z, cur.q[1].w, cur.q[2].x,
+                                                     cur.q[2].y, cur.q[2].z, cur.q[2].w, cur.q[3].x, cur.q[3].y};
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 128);
             const uint32_t h_tmem = tmem_base + (uint32_t)(256 + t * 128);
             // the epilogue of the accumulator's previous user has loaded it into registers
             T2_WAIT(1, mbar_wait(bar_acc_free + 8 * acc, (free_bits >> acc) & 1u));
             free_bits ^= 1u << acc;
-            if (sl.flags & SLOT_WAIT_H) {   // the previous layer's activations are written
+            if (hdr & (1u << 18)) {   // the previous layer's activations are written
               T2_WAIT(2, mbar_wait(bar_h_ready + 8 * t, (h_bits >> t) & 1u));
               h_bits ^= 1u << t;
             }
             tc_fence_after();
-            for (int gi = 0; gi < Ly.ngroups; ++gi) {
-              const int grp = Ly.groups[gi];
-              const int cnt = (grp >> 5) & 7;
-              const bool from_h = (grp >> 8) & 1;
-              // Operand words are formed BEFORE the barrier waits (the empty asm pins them there): whatever sits between a
-              // satisfied wait and the tcgen05.mma instructions is pure latency on the slot-to-slot dependency chain.
-              const uint32_t b_lo0 = ring16 + stage * (T2_STAGE_BYTES >> 4);
-              const uint32_t a_base = from_h ? h_tmem : xs16;
-              uint32_t a_w[T2_STAGE_SLABS], b_w[T2_STAGE_SLABS];
 #pragma unroll
-              for (int i2 = 0; i2 < T2_STAGE_SLABS; ++i2) {
-                a_w[i2] = a_base + Ly.a_rel[gi][i2];
-                b_w[i2] = b_lo0 + (uint32_t)i2 * hb16;
-              }
-              uint32_t accum = (gi > 0) ? 1u : 0u;
-              asm volatile("" ::"r"(a_w[0]), "r"(a_w[1]), "r"(a_w[2]), "r"(a_w[3]), "r"(b_w[0]), "r"(b_w[1]), "r"(b_w[2]), "r"(b_w[3]), "r"(accum), "r"(d_tmem), "r"(idesc));
-              if (gi == 0 && (sl.flags & SLOT_WAIT_XS)) {   // XS holds this tile's X
-                T2_WAIT(3, mbar_wait(bar_xs_ready, xs_phase));
-                xs_phase ^= 1;
-              }
-              T2_WAIT(4, mbar_wait(bar_full + 8 * stage, phase));
-              tc_fence_after();
+            for (int gi = 0; gi < T2_REC_GROUPS; ++gi) {
+              if (gi < ngroups) {
+                const uint32_t gm = (gmeta >> (4 * gi)) & 15u;
+                const int cnt = (int)(gm & 7u);
+                const bool from_h = (gm >> 3) != 0;
+                // Operand words are formed BEFORE the barrier waits (the empty asm pins them there): whatever sits between
+                // a satisfied wait and the tcgen05.mma instructions is pure latency on the slot-to-slot dependency chain.
+                const uint32_t b_lo0 = ring16 + stage * (T2_STAGE_BYTES >> 4);
+                const uint32_t a_base = from_h ? h_tmem : xs16;
+                uint32_t a_w[T2_STAGE_SLABS], b_w[T2_STAGE_SLABS];
+#pragma unroll
+                for (int i2 = 0; i2 < T2_STAGE_SLABS; ++i2) {
+                  a_w[i2] = a_base + ((rel[2 * gi + (i2 >> 1)] >> (16 * (i2 & 1))) & 0xffffu);
+                  b_w[i2] = b_lo0 + (uint32_t)i2 * hb16;
+                }
+                uint32_t accum = (gi > 0) ? 1u : 0u;
+                asm volatile("" ::"r"(a_w[0]), "r"(a_w[1]), "r"(a_w[2]), "r"(a_w[3]), "r"(b_w[0]), "r"(b_w[1]), "r"(b_w[2]), "r"(b_w[3]), "r"(accum), "r"(d_tmem), "r"(idesc));
+                if (gi == 0 && (hdr & (1u << 19))) {   // XS holds this tile's X
+                  T2_WAIT(3, mbar_wait(bar_xs_ready, xs_phase));
+                  xs_phase ^= 1;
+                }
+                T2_WAIT(4, mbar_wait(bar_full + 8 * stage, phase));
+                tc_fence_after();
 #ifdef ONERF_WAITSTATS
-              const long long mi0 = clock64();
+                const long long mi0 = clock64();
 #endif
-              if (elect_one()) {
+                if (elect_one()) {
 #ifndef T2_EXP_NO_MMA
-              if (!from_h) {
+                  if (!from_h) {
 #pragma unroll
-                for (int i2 = 0; i2 < T2_STAGE_SLABS; ++i2) {
-                  if (i2 < cnt) {
-                    umma_bf16(d_tmem, make_desc_hl(a_w[i2], DESC_HI_SW128), make_desc_hl(b_w[i2], DESC_HI_SW64), idesc, accum);
-                    umma_bf16(d_tmem, make_desc_hl(a_w[i2] + 2u, DESC_HI_SW128), make_desc_hl(b_w[i2] + 2u, DESC_HI_SW64), idesc, 1u);
-                    accum = 1u;
-                  }
-                }
-              } else {
+                    for (int i2 = 0; i2 < T2_STAGE_SLABS; ++i2) {
+                      if (i2 < cnt) {
+                        umma_bf16(d_tmem, make_desc_hl(a_w[i2], DESC_HI_SW128), make_desc_hl(b_w[i2], DESC_HI_SW64), idesc, accum);
+                        umma_bf16(d_tmem, make_desc_hl(a_w[i2] + 2u, DESC_HI_SW128), make_desc_hl(b_w[i2] + 2u, DESC_HI_SW64), idesc, 1u);
+                        accum = 1u;
+                      }
+                    }
+                  } else {
 #pragma unroll
-                for (int i2 = 0; i2 < T2_STAGE_SLABS; ++i2) {
-                  if (i2 < cnt) {
-                    umma_bf16_ts(d_tmem, a_w[i2], make_desc_hl(b_w[i2], DESC_HI_SW64), idesc, accum);
-                    umma_bf16_ts(d_tmem, a_w[i2] + 8u, make_desc_hl(b_w[i2] + 2u, DESC_HI_SW64), idesc, 1u);
-                    accum = 1u;
+                    for (int i2 = 0; i2 < T2_STAGE_SLABS; ++i2) {
+                      if (i2 < cnt) {
+                        umma_bf16_ts(d_tmem, a_w[i2], make_desc_hl(b_w[i2], DESC_HI_SW64), idesc, accum);
+                        umma_bf16_ts(d_tmem, a_w[i2] + 8u, make_desc_hl(b_w[i2] + 2u, DESC_HI_SW64), idesc, 1u);
+                        accum = 1u;
+                      }
+                    }
                   }
-                }
-              }
 #endif
 #ifdef ONERF_WAITSTATS
-              const long long mi1 = clock64();
-              wstat[5] += mi1 - mi0;
+                  const long long mi1 = clock64();
+                  wstat[5] += mi1 - mi0;
 #endif
-              umma_commit(bar_empty + 8 * stage);
-              if (gi == Ly.ngroups - 1) umma_commit(bar_acc_ready + 8 * acc);
+                  umma_commit(bar_empty + 8 * stage);
+                  if (gi == ngroups - 1) umma_commit(bar_acc_ready + 8 * acc);
 #ifdef ONERF_WAITSTATS
-              wstat[7] += clock64() - mi1;
+                  wstat[7] += clock64() - mi1;
 #endif
+                }
+                __syncwarp();
+                if (++stage == T2_NSTAGE) { stage = 0; phase ^= 1; }
               }
-              __syncwarp();
-              if (++stage == T2_NSTAGE) { stage = 0; phase ^= 1; }
             }
+            cur = nxt;
           }
         }
       }
@@ -739,6 +754,24 @@ int onerf_launch_field_bf16_two_tile(onerf_ctx* ctx, const FieldParams& fp, cuda
   }
   P.n_slots = ns;
   P.n_xuse = nx;
+  for (int i = 0; i < ns; ++i) {
+    const T2Slot& sl = P.slots[i];
+    const T2Layer& t = P.layers[sl.layer];
+    if (t.ngroups > T2_REC_GROUPS) {
+      onerf_set_error("two-tile field kernel: a layer needs %d ring stages per slot (max %d)", t.ngroups, T2_REC_GROUPS);
+      return ONERF_ERR_UNSUPPORTED;
+    }
+    const uint32_t half_bytes = ((uint32_t)t.N * 64u) >> (t.nhalf - 1);
+    uint32_t w[16] = {0};
+    w[0] = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((t.N >> (t.nhalf - 1)) >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);   // = make_idesc
+    w[1] = (half_bytes >> 4) | ((uint32_t)(sl.flags >> 4) << 16) | ((uint32_t)sl.tile << 17) |
+           ((sl.flags & SLOT_WAIT_H) ? 1u << 18 : 0u) | ((sl.flags & SLOT_WAIT_XS) ? 1u << 19 : 0u) | ((uint32_t)t.ngroups << 20);
+    for (int g = 0; g < t.ngroups; ++g) {
+      w[2] |= ((uint32_t)((t.groups[g] >> 5) & 7) | ((uint32_t)((t.groups[g] >> 8) & 1) << 3)) << (4 * g);
+      for (int i2 = 0; i2 < T2_STAGE_SLABS; ++i2) w[4 + 2 * g + (i2 >> 1)] |= (t.a_rel[g][i2] & 0xffffu) << (16 * (i2 & 1));
+    }
+    for (int q = 0; q < 4; ++q) P.rec[i].q[q] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+  }
   // The epilogue's program: one event per slot, in slot order, plus the X productions.  XS is one buffer:
   //   X of tile A for X-fed layer l  : right after A's last event of layer l - 1 (first event of the pair for layer 0); the
   //                                    previous reader of XS (tile B, an earlier layer) has long completed
