@@ -240,8 +240,13 @@ __device__ __forceinline__ void epi_event(const T2Params& P, const uint4 e, uint
   tc_fence_after();
   // per-row metadata of this pair, written by the encode warps before the pair's first X was produced (read it only
   // after an accumulator of the pair is ready: that orders it after the gather)
-  const int2 meta = *reinterpret_cast<const int2*>(smem + OFF_META + ((parity * 2 + T) * 128 + row) * 8);
-  const float* rc = p.ray_const + (int64_t)meta.x * ONERF_RAY_CONST_FLOATS + e.z + cq * ncol;   // per-ray constants of this thread's columns
+  // (only the two event kinds with per-ray constants touch it: the common hidden-layer event does no address arithmetic)
+  int2 meta = make_int2(0, 0);
+  const float* rc = nullptr;
+  if (kind == EPI_DIR || kind == EPI_HIDDEN_RC) {
+    meta = *reinterpret_cast<const int2*>(smem + OFF_META + ((parity * 2 + T) * 128 + row) * 8);
+    rc = p.ray_const + (int64_t)meta.x * ONERF_RAY_CONST_FLOATS + e.z + cq * ncol;   // per-ray constants of this thread's columns
+  }
   uint32_t v[32];
 #ifdef ONERF_WAITSTATS
   const long long ph0 = clock64();
@@ -612,8 +617,10 @@ __global__ void __launch_bounds__(T2_THREADS, 1) field_tc2_kernel(const __grid_c
     int parity = 0;
     for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, parity ^= 1) {
 #pragma unroll 1
+      uint4 e_next = P.ev_tab[0];
       for (int ei = 0; ei < P.n_events; ++ei) {
-        const uint4 e = P.ev_tab[ei];
+        const uint4 e = e_next;
+        e_next = P.ev_tab[(ei + 1 == P.n_events) ? 0 : ei + 1];   // one event ahead: the table read hides behind this event
         if ((e.w & 0xffu) == EV_XGEN) {
           // ---- X of one tile into XS: row = thread & 127, the four column quarters of the CTA take one block each ----
           const int xf = (int)(e.w >> 8), t = xf & XG_TILE;
