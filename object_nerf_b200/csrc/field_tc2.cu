@@ -268,18 +268,23 @@ __device__ __forceinline__ void epi_event(const T2Params& P, const uint4 e, uint
     float part0 = 0.0f, part1 = 0.0f, part2 = 0.0f;
     if (ncol == 32) math_dir<32>(v, rc, headw, N, part0, part1, part2);
     else math_dir<16>(v, rc, headw, N, part0, part1, part2);
-    // combine the four column quarters of this row through shared memory (one quantity per round: the scratch is 2 KB),
-    // finish the heads, write out
-    float* scratch = reinterpret_cast<float*>(smem + OFF_SCRATCH);
-    float tot[4];
-    const float mine[4] = {T ? sigma_b : sigma_a, part0, part1, part2};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      scratch[cq * 128 + row] = mine[k];
-      asm volatile("bar.sync 1, %0;" ::"n"(T2_EPI_THREADS) : "memory");
-      tot[k] = scratch[row] + scratch[128 + row] + scratch[256 + row] + scratch[384 + row];
-      asm volatile("bar.sync 1, %0;" ::"n"(T2_EPI_THREADS) : "memory");
+    // combine the four column quarters of this row through shared memory: one float4 per thread, one exchange.  The
+    // scratch is the last atom of XS (columns 320..383: only the object layers' X lives there, their MMAs completed long
+    // ago, and the next object X is written after every warp has passed this event's barrier); the two tiles use
+    // different halves, so the other tile's head event, which follows immediately, cannot overwrite what is being read.
+    float4* scratch = reinterpret_cast<float4*>(smem + OFF_X + 5 * ATOM_BYTES) + T * 512;
+    scratch[cq * 128 + row] = make_float4(T ? sigma_b : sigma_a, part0, part1, part2);
+    asm volatile("bar.sync 1, %0;" ::"n"(T2_EPI_THREADS) : "memory");
+    float tot[4] = {0.f, 0.f, 0.f, 0.f};
+    if (cq == 0) {
+      const float4 q0 = scratch[row], q1 = scratch[128 + row], q2 = scratch[256 + row], q3 = scratch[384 + row];
+      tot[0] = q0.x + q1.x + q2.x + q3.x;   // (same order of additions as before: bit-identical results)
+      tot[1] = q0.y + q1.y + q2.y + q3.y;
+      tot[2] = q0.z + q1.z + q2.z + q3.z;
+      tot[3] = q0.w + q1.w + q2.w + q3.w;
     }
+    // (the reads above are done before any warp can reach the next production of an object X, which rewrites this atom)
+    asm volatile("bar.sync 1, %0;" ::"n"(T2_EPI_THREADS) : "memory");
     if (cq == 0 && (meta.y & (1 << 30))) {
       const float* hb = Pf + (branch ? p.L.orgb_b : p.L.rgb_b);
       float sg = tot[0] + __ldg(Pf + (branch ? p.L.osigma_b : p.L.sigma_b));
