@@ -59,29 +59,6 @@ struct TcParams {
   TrainLayout TL;
 };
 
-// where one thread's output of one layer half goes in the training dump
-struct DumpDst {
-  uint8_t* row;      // byte address of (tile, atom 0, this row) of the layer's activation slot; null = no dump
-  uint32_t* mask;    // &masks[tile][word 0 of the layer][this row], stride 128 words per mask word; null = no mask
-  int swz;           // row & 7
-};
-// store NP packed bf16 pairs (columns n .. n + 2 NP - 1 of the layer) and their sign bits
-template <int NP>
-__device__ __forceinline__ void dump_packed(const DumpDst& d, int n, int word, const uint32_t* pk) {
-  if (d.row == nullptr) return;
-  uint8_t* base = d.row + (size_t)(n >> 6) * ATOM_BYTES;
-  const int chunk0 = (n & 63) >> 3;
-#pragma unroll
-  for (int j = 0; j < NP / 4; ++j)
-    *reinterpret_cast<uint4*>(base + (((chunk0 + j) ^ d.swz) << 4)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-  if (d.mask) {
-    uint32_t m = 0;
-#pragma unroll
-    for (int j = 0; j < NP; ++j) m |= (((~pk[j]) >> 15) & 1u) << (2 * j) | ((~pk[j]) >> 31) << (2 * j + 1);
-    d.mask[word * 128] = m;
-  }
-}
-
 // ------------------------------------------------------------------------------------------------
 // epilogue of one layer half for one thread: NC accumulator columns of its row
 // ------------------------------------------------------------------------------------------------
@@ -390,13 +367,17 @@ static long long* g_timeline = nullptr;
 extern "C" void onerf_debug_timeline(void* dev_buf) { g_timeline = reinterpret_cast<long long*>(dev_buf); }
 
 int onerf_launch_field_bf16_two_tile(onerf_ctx* ctx, const FieldParams& fp, cudaStream_t stream);   // field_tc2.cu
+static int g_force_one_tile = -1;   // -1: take ONERF_TC_ONE_TILE from the environment at the first launch
+extern "C" void onerf_debug_force_one_tile(int on) { g_force_one_tile = on ? 1 : 0; }
 
 int onerf_launch_field_bf16(onerf_ctx* ctx, const FieldParams& fp, cudaStream_t stream) {
   const PackLayout& L = fp.L;
-  // The voxel model's inference forward runs on the two-tile kernel (field_tc2.cu).  This one-tile kernel serves the
-  // plain-PE model and the training forward (activation dump); ONERF_TC_ONE_TILE=1 forces it everywhere (A/B runs).
-  static const int one_tile = [] { const char* v = getenv("ONERF_TC_ONE_TILE"); return (v && v[0] == '1') ? 1 : 0; }();
-  if (L.use_voxel && !fp.train_ws && !one_tile) return onerf_launch_field_bf16_two_tile(ctx, fp, stream);
+  // The voxel model's forward runs on the two-tile kernel (field_tc2.cu): inference, and the training forward (activation
+  // dump) when both branches are evaluated.  This one-tile kernel serves the plain-PE model and single-branch training
+  // dumps; ONERF_TC_ONE_TILE=1 / onerf_debug_force_one_tile(1) force it everywhere (A/B runs, bitwise dump comparison).
+  if (g_force_one_tile < 0) { const char* v = getenv("ONERF_TC_ONE_TILE"); g_force_one_tile = (v && v[0] == '1') ? 1 : 0; }
+  if (L.use_voxel && !g_force_one_tile && (!fp.train_ws || (fp.want_scene && fp.want_object)))
+    return onerf_launch_field_bf16_two_tile(ctx, fp, stream);
   TcParams P;
   memset(&P, 0, sizeof(P));
   P.f = fp;

@@ -69,6 +69,7 @@ struct T2Layer {
   int nslab_x, nslab_h;
   int epi, branch, rc_base;
   int writes_h;     // the epilogue leaves activations for the next layer (everything except the dir layers)
+  int act_slot;     // training dump: activation slot of the layer's outputs (layout.h: TrainLayout)
   int64_t img_off, bias_off;
   int ngroups, n_xgroups;
   int groups[T2_MAX_GROUPS];   // bits [0,5) first slab (inside X or H), [5,8) slab count (1..4), bit 8: from H
@@ -108,6 +109,13 @@ struct T2Params {
   //   x: accumulator whose completion says that XS is free (the last slot of the other tile's X-fed layer), 0xff: none
   uint4 ev_tab[T2_MAX_EVENTS];
   int n_events;
+  // training forward (kernel template DUMP): where the event's activations go in the training workspace
+  //   ev_dump[i] = (activation slot + 1) | (first mask word + 1) << 8   (0 in a field: nothing to store)
+  // T2Rec header bit 28: the slot's X is also the tile's dump of X (bulk store by the MMA warp), bit 29: drain that copy
+  // before the slot's accumulator is announced complete (the next production of X waits for exactly that)
+  uint32_t ev_dump[T2_MAX_EVENTS];
+  uint8_t* dump;
+  TrainLayout TL;
 };
 enum SlotEpi { SE_KIND = 7, SE_TWO = 8, SE_H1 = 16, SE_TILE = 32, SE_BRANCH = 64, SE_N64 = 128 };
 enum XgenFlags { XG_TILE = 1, XG_FULL = 2, XG_WAIT_F = 4, XG_RELEASE_F = 8 };
@@ -183,6 +191,27 @@ __device__ __forceinline__ void math_dir(const uint32_t* v, const float* rcbias,
   }
 }
 
+// training forward: the same, and the activations packed for the dump (they feed the rgb head's weight gradient)
+template <int NC>
+__device__ __forceinline__ void math_dir_pk(const uint32_t* v, const float* rcbias, const float* headw, int head_ld, float& p0,
+                                            float& p1, float& p2, uint32_t* pk) {
+#pragma unroll
+  for (int j4 = 0; j4 < NC / 4; ++j4) {
+    const float4 b = __ldg(reinterpret_cast<const float4*>(rcbias) + j4);
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(headw) + j4);
+    const float4 w1 = __ldg(reinterpret_cast<const float4*>(headw + head_ld) + j4);
+    const float4 w2 = __ldg(reinterpret_cast<const float4*>(headw + 2 * head_ld) + j4);
+    float t0 = __uint_as_float(v[4 * j4 + 0]) + b.x, t1 = __uint_as_float(v[4 * j4 + 1]) + b.y;
+    float t2 = __uint_as_float(v[4 * j4 + 2]) + b.z, t3 = __uint_as_float(v[4 * j4 + 3]) + b.w;
+    t0 = fmaxf(t0, t0 * kLeaky); t1 = fmaxf(t1, t1 * kLeaky); t2 = fmaxf(t2, t2 * kLeaky); t3 = fmaxf(t3, t3 * kLeaky);
+    p0 = fmaf(t0, w0.x, p0); p0 = fmaf(t1, w0.y, p0); p0 = fmaf(t2, w0.z, p0); p0 = fmaf(t3, w0.w, p0);
+    p1 = fmaf(t0, w1.x, p1); p1 = fmaf(t1, w1.y, p1); p1 = fmaf(t2, w1.z, p1); p1 = fmaf(t3, w1.w, p1);
+    p2 = fmaf(t0, w2.x, p2); p2 = fmaf(t1, w2.y, p2); p2 = fmaf(t2, w2.z, p2); p2 = fmaf(t3, w2.w, p2);
+    pk[2 * j4] = pack_bf16(t0, t1);
+    pk[2 * j4 + 1] = pack_bf16(t2, t3);
+  }
+}
+
 // A non-dir layer half is 128 wide: 32 accumulator columns per thread, consumed in two batches of 16 (16 live registers
 // instead of 32); after the last load the accumulator is handed back.  Returns the partial sigma dot product.
 __device__ __forceinline__ float epi_batches(int epi, uint32_t acc_addr, const float* bias, const float* rcbias,
@@ -220,7 +249,9 @@ constexpr uint32_t T2_SMEM_BYTES = OFF_BAR + 256 + 1024;
 // One epilogue event (slot `si` of the pair's program).  Live state across events: the 16-register stash, two partial
 // sigma sums and the barrier phase bits; everything else comes from the slot table (constant bank) and the per-row
 // metadata the encode warps left in shared memory.
-__device__ __forceinline__ void epi_event(const T2Params& P, const uint4 e, uint8_t* smem, uint32_t sbase, uint32_t lane_taddr,
+template <bool DUMP>
+__device__ __forceinline__ void epi_event(const T2Params& P, const uint4 e, uint32_t ed, int64_t tile_idx, int64_t n_tiles,
+                                          uint8_t* smem, uint32_t sbase, uint32_t lane_taddr,
                                           int parity, uint32_t (&stash)[16], uint32_t& acc_bits, float& sigma_a, float& sigma_b
 #ifdef ONERF_WAITSTATS
                                           , long long* wstat
@@ -263,11 +294,26 @@ __device__ __forceinline__ void epi_event(const T2Params& P, const uint4 e, uint
   wstat[0] += ph1 - ph0;
   if (kind == EPI_DIR) wstat[4] -= ph1; else if ((flags & SE_TWO) && !(flags & SE_H1)) wstat[1] -= ph1; else wstat[2] -= ph1;
 #endif
+  // training forward: this thread's row of the layer's activation slot and of its mask words
+  DumpDst dd;
+  dd.row = nullptr; dd.mask = nullptr; dd.swz = row & 7;
+  const int half = (flags & SE_H1) ? 1 : 0, dword = half * 4 + cq, dcol = half * 128 + cq * ncol;
+  if (DUMP && (ed & 0xffu) != 0u && tile_idx < n_tiles) {
+    const int slot = (int)(ed & 0xffu) - 1, mw = (int)((ed >> 8) & 0xffu) - 1;
+    dd.row = P.dump + P.TL.act_off[slot] + ((size_t)tile_idx * P.TL.act_atoms[slot]) * ATOM_BYTES + (size_t)row * 128;
+    if (mw >= 0) dd.mask = reinterpret_cast<uint32_t*>(P.dump + P.TL.mask_off) + ((size_t)tile_idx * ONERF_MASK_WORDS + mw) * 128 + row;
+  }
   if (kind == EPI_DIR) {
     const float* headw = Pf + (branch ? p.L.orgb_w : p.L.rgb_w) + cq * ncol;
     float part0 = 0.0f, part1 = 0.0f, part2 = 0.0f;
-    if (ncol == 32) math_dir<32>(v, rc, headw, N, part0, part1, part2);
-    else math_dir<16>(v, rc, headw, N, part0, part1, part2);
+    if (DUMP) {
+      uint32_t dpk[16];
+      if (ncol == 32) { math_dir_pk<32>(v, rc, headw, N, part0, part1, part2, dpk); dump_packed<16>(dd, dcol, dword, dpk); }
+      else { math_dir_pk<16>(v, rc, headw, N, part0, part1, part2, dpk); dump_packed<8>(dd, dcol, dword, dpk); }
+    } else {
+      if (ncol == 32) math_dir<32>(v, rc, headw, N, part0, part1, part2);
+      else math_dir<16>(v, rc, headw, N, part0, part1, part2);
+    }
     // combine the four column quarters of this row through shared memory: one float4 per thread, one exchange.  The
     // scratch is the last atom of XS (columns 320..383: only the object layers' X lives there, their MMAs completed long
     // ago, and the next object X is written after every warp has passed this event's barrier); the two tiles use
@@ -322,6 +368,7 @@ __device__ __forceinline__ void epi_event(const T2Params& P, const uint4 e, uint
       default: part = math_hidden_sigma<32>(v, bias, Pf + (branch ? p.L.osigma_w : p.L.sigma_w) + cq * 32, stash); break;
     }
     if (kind == EPI_HIDDEN_SIGMA) { if (T) sigma_b = part; else sigma_a = part; }
+    if (DUMP) dump_packed<16>(dd, dcol, dword, stash);
 #ifdef ONERF_WAITSTATS
     asm volatile("" ::"r"(stash[0]), "r"(stash[15]));
     wstat[1] += clock64();
@@ -355,6 +402,7 @@ __device__ __forceinline__ void epi_event(const T2Params& P, const uint4 e, uint
   wstat[2] += ph2;
 #endif
   tmem_st16(h_addr + out_col, pk);
+  if (DUMP) dump_packed<16>(dd, dcol, dword, pk);
   tmem_st_wait();
   tc_fence_before();
   __syncwarp();
@@ -400,6 +448,7 @@ __device__ __forceinline__ void gather_tile(const FieldParams& p, const GridView
   F[24 * 128] = x; F[25 * 128] = y; F[26 * 128] = z;
 }
 
+template <bool DUMP>
 __global__ void __launch_bounds__(T2_THREADS, 1) field_tc2_kernel(const __grid_constant__ T2Params P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const FieldParams& p = P.f;
@@ -505,7 +554,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) field_tc2_kernel(const __grid_c
             const T2Rec nxt = P.rec[(si + 1 == P.n_slots) ? 0 : si + 1];   // in flight while this slot waits and issues
             const uint32_t idesc = cur.q[0].x, hdr = cur.q[0].y, gmeta = cur.q[0].z;
             const uint32_t hb16 = hdr & 0xffffu;
-            const int acc = (hdr >> 16) & 1, t = (hdr >> 17) & 1, ngroups = (int)(hdr >> 20);
+            const int acc = (hdr >> 16) & 1, t = (hdr >> 17) & 1, ngroups = (int)((hdr >> 20) & 0xffu);
             const uint32_t rel[2 * T2_REC_GROUPS] = {cur.q[1].x, cur.q[1].y, cur.q[1].z, cur.q[1].w, cur.q[2].x,
                                                      cur.q[2].y, cur.q[2].z, cur.q[2].w, cur.q[3].x, cur.q[3].y};
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 128);
@@ -539,6 +588,13 @@ __global__ void __launch_bounds__(T2_THREADS, 1) field_tc2_kernel(const __grid_c
                 if (gi == 0 && (hdr & (1u << 19))) {   // XS holds this tile's X
                   T2_WAIT(3, mbar_wait(bar_xs_ready, xs_phase));
                   xs_phase ^= 1;
+                  if (DUMP && (hdr & (1u << 28)) && 2 * pair + t < n_tiles) {   // training: the tile's X atoms -> workspace
+                    if (elect_one()) {
+                      bulk_s2g(P.dump + P.TL.act_off[0] + (size_t)(2 * pair + t) * 6 * ATOM_BYTES, sX, 6u * ATOM_BYTES);
+                      bulk_commit_group();
+                    }
+                    __syncwarp();
+                  }
                 }
                 T2_WAIT(4, mbar_wait(bar_full + 8 * stage, phase));
                 tc_fence_after();
@@ -572,7 +628,10 @@ __global__ void __launch_bounds__(T2_THREADS, 1) field_tc2_kernel(const __grid_c
                   wstat[5] += mi1 - mi0;
 #endif
                   umma_commit(bar_empty + 8 * stage);
-                  if (gi == ngroups - 1) umma_commit(bar_acc_ready + 8 * acc);
+                  if (gi == ngroups - 1) {
+                    if (DUMP && (hdr & (1u << 29))) bulk_wait_group_read0();   // XS may be rewritten once this accumulator is seen
+                    umma_commit(bar_acc_ready + 8 * acc);
+                  }
 #ifdef ONERF_WAITSTATS
                   wstat[7] += clock64() - mi1;
 #endif
@@ -660,7 +719,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1) field_tc2_kernel(const __grid_c
 #endif
           continue;
         }
-        epi_event(P, e, gen_base, sbase, lane_taddr, parity, stash, acc_bits, sigma_a, sigma_b
+        epi_event<DUMP>(P, e, DUMP ? P.ev_dump[ei] : 0u, 2 * pair + ((e.w & SE_TILE) ? 1 : 0), n_tiles, gen_base, sbase, lane_taddr,
+                        parity, stash, acc_bits, sigma_a, sigma_b
 #ifdef ONERF_WAITSTATS
                   , wstat
 #endif
@@ -677,6 +737,10 @@ __global__ void __launch_bounds__(T2_THREADS, 1) field_tc2_kernel(const __grid_c
   }
 #endif
   // ---- teardown ----
+  if (DUMP && warp == T2_MMA_WARP) {   // (the elected lane of an elect region is the same lane every time)
+    if (elect_one()) bulk_wait_group0();
+    __syncwarp();
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == T2_MMA_WARP) tmem_dealloc(tmem_base, 512);
@@ -695,8 +759,9 @@ int onerf_launch_field_bf16_two_tile(onerf_ctx* ctx, const FieldParams& fp, cuda
   P.timeline = g_timeline2;
   const int xs = L.KX / 32, xo = L.KO / 32;
   int n = 0;
-  auto add = [&](int gemm, int nx, int nh, int epi, int branch, int rc_base) {
+  auto add = [&](int gemm, int nx, int nh, int epi, int branch, int rc_base, int act_slot) {
     T2Layer& t = P.layers[n++];
+    t.act_slot = act_slot;
     t.N = L.g[gemm].N; t.nhalf = t.N > 128 ? 2 : 1;
     t.nslab_x = nx; t.nslab_h = nh; t.epi = epi; t.branch = branch; t.rc_base = rc_base;
     t.writes_h = epi != EPI_DIR;
@@ -721,24 +786,24 @@ int onerf_launch_field_bf16_two_tile(onerf_ctx* ctx, const FieldParams& fp, cuda
   // Object branch first: a pair's raw features can only be replaced (by the gather of the NEXT pair, ~27K cycles on two
   // warps) after the tile's last X-fed layer; with the scene branch last that layer is S4 and ten long slots still follow.
   if (fp.want_object) {
-    add(G_O0, xo, 0, EPI_HIDDEN_RC, 1, RC_OL0);
-    add(G_O1, 0, 4, EPI_HIDDEN, 1, 0);
-    add(G_O2, xo, 4, EPI_HIDDEN_RC, 1, RC_OL2);
-    add(G_O3, 0, 4, EPI_HIDDEN_SIGMA, 1, 0);
-    add(G_OFIN, 0, 4, EPI_FINAL, 1, 0);
-    add(G_ODIR, 0, 4, EPI_DIR, 1, RC_ODIR);
+    add(G_O0, xo, 0, EPI_HIDDEN_RC, 1, RC_OL0, 11);
+    add(G_O1, 0, 4, EPI_HIDDEN, 1, 0, 12);
+    add(G_O2, xo, 4, EPI_HIDDEN_RC, 1, RC_OL2, 13);
+    add(G_O3, 0, 4, EPI_HIDDEN_SIGMA, 1, 0, 14);
+    add(G_OFIN, 0, 4, EPI_FINAL, 1, 0, 15);
+    add(G_ODIR, 0, 4, EPI_DIR, 1, RC_ODIR, 16);
   }
   if (fp.want_scene) {
-    add(G_S0, xs, 0, EPI_HIDDEN, 0, 0);
-    add(G_S1, 0, 8, EPI_HIDDEN, 0, 0);
-    add(G_S2, 0, 8, EPI_HIDDEN, 0, 0);
-    add(G_S3, 0, 8, EPI_HIDDEN, 0, 0);
-    add(G_S4, xs, 8, EPI_HIDDEN, 0, 0);
-    add(G_S5, 0, 8, EPI_HIDDEN, 0, 0);
-    add(G_S6, 0, 8, EPI_HIDDEN, 0, 0);
-    add(G_S7, 0, 8, EPI_HIDDEN_SIGMA, 0, 0);
-    add(G_SFIN, 0, 8, EPI_FINAL, 0, 0);
-    add(G_SDIR, 0, 8, EPI_DIR, 0, RC_SDIR);
+    add(G_S0, xs, 0, EPI_HIDDEN, 0, 0, 1);
+    add(G_S1, 0, 8, EPI_HIDDEN, 0, 0, 2);
+    add(G_S2, 0, 8, EPI_HIDDEN, 0, 0, 3);
+    add(G_S3, 0, 8, EPI_HIDDEN, 0, 0, 4);
+    add(G_S4, xs, 8, EPI_HIDDEN, 0, 0, 5);
+    add(G_S5, 0, 8, EPI_HIDDEN, 0, 0, 6);
+    add(G_S6, 0, 8, EPI_HIDDEN, 0, 0, 7);
+    add(G_S7, 0, 8, EPI_HIDDEN_SIGMA, 0, 0, 8);
+    add(G_SFIN, 0, 8, EPI_FINAL, 0, 0, 9);
+    add(G_SDIR, 0, 8, EPI_DIR, 0, RC_SDIR, 10);
   }
   P.n_layers = n;
   // slots of one tile pair
@@ -778,6 +843,11 @@ int onerf_launch_field_bf16_two_tile(onerf_ctx* ctx, const FieldParams& fp, cuda
     w[0] = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((t.N >> (t.nhalf - 1)) >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);   // = make_idesc
     w[1] = (half_bytes >> 4) | ((uint32_t)(sl.flags >> 4) << 16) | ((uint32_t)sl.tile << 17) |
            ((sl.flags & SLOT_WAIT_H) ? 1u << 18 : 0u) | ((sl.flags & SLOT_WAIT_XS) ? 1u << 19 : 0u) | ((uint32_t)t.ngroups << 20);
+    // training dump of X: at the tile's FIRST X-fed layer (the object branch's O0: all 384 columns are produced there)
+    if (fp.train_ws && sl.layer == 0 && t.nslab_x > 0) {
+      if (sl.flags & SLOT_WAIT_XS) w[1] |= 1u << 28;
+      if (sl.half == t.nhalf - 1) w[1] |= 1u << 29;
+    }
     for (int g = 0; g < t.ngroups; ++g) {
       w[2] |= ((uint32_t)((t.groups[g] >> 5) & 7) | ((uint32_t)((t.groups[g] >> 8) & 1) << 3)) << (4 * g);
       for (int i2 = 0; i2 < T2_STAGE_SLABS; ++i2) w[4 + 2 * g + (i2 >> 1)] |= (t.a_rel[g][i2] & 0xffffu) << (16 * (i2 & 1));
@@ -809,6 +879,7 @@ int onerf_launch_field_bf16_two_tile(onerf_ctx* ctx, const FieldParams& fp, cuda
     P.ev_tab[ne].y = (uint32_t)(t.bias_off + sl.half * 128);
     P.ev_tab[ne].z = (uint32_t)(t.rc_base + sl.half * 128);
     P.ev_tab[ne].w = flags | ((uint32_t)acc << 16) | ((uint32_t)t.N << 20);
+    P.ev_dump[ne] = (uint32_t)(t.act_slot + 1) | ((uint32_t)(onerf_mask_word0(t.act_slot) + 1) << 8);
     ++ne;
     if (sl.tile == 0 && last_slot_of_layer && sl.layer + 1 < n && P.layers[sl.layer + 1].nslab_x > 0) xgen(0, xi, 0xffu);
   }
@@ -817,8 +888,19 @@ int onerf_launch_field_bf16_two_tile(onerf_ctx* ctx, const FieldParams& fp, cuda
   const int64_t tiles = (total + TM - 1) / TM, pairs = (tiles + 1) / 2;
   const int blocks = (int)(pairs < ctx->num_sms ? pairs : ctx->num_sms);
   const size_t smem = T2_SMEM_BYTES;
-  ONERF_CUDA(cudaFuncSetAttribute(field_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  field_tc2_kernel<<<blocks, T2_THREADS, smem, stream>>>(P);
+  if (fp.train_ws) {   // training forward: both branches, the object branch's first layer produces all of X
+    if (!(fp.want_scene && fp.want_object)) {
+      onerf_set_error("two-tile field kernel: the training dump needs both branches");
+      return ONERF_ERR_UNSUPPORTED;
+    }
+    P.dump = reinterpret_cast<uint8_t*>(fp.train_ws);
+    P.TL = onerf_make_train_layout(L.use_voxel, total);
+    ONERF_CUDA(cudaFuncSetAttribute(field_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    field_tc2_kernel<true><<<blocks, T2_THREADS, smem, stream>>>(P);
+  } else {
+    ONERF_CUDA(cudaFuncSetAttribute(field_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    field_tc2_kernel<false><<<blocks, T2_THREADS, smem, stream>>>(P);
+  }
   ONERF_LAUNCH_CHECK(ctx);
   return ONERF_OK;
 }
