@@ -751,9 +751,9 @@ __global__ void __launch_bounds__(T2_THREADS, 1) field_tc2_kernel(const __grid_c
 static long long* g_timeline2 = nullptr;
 extern "C" void onerf_debug_timeline2(void* dev_buf) { g_timeline2 = reinterpret_cast<long long*>(dev_buf); }
 
-int onerf_launch_field_bf16_two_tile(onerf_ctx* ctx, const FieldParams& fp, cudaStream_t stream) {
+// The static program of one tile pair (host): layers, MMA slots and their 64-byte records, the epilogue's event table.
+static int t2_build_program(const FieldParams& fp, T2Params& P) {
   const PackLayout& L = fp.L;
-  T2Params P;
   memset(&P, 0, sizeof(P));
   P.f = fp;
   P.timeline = g_timeline2;
@@ -884,6 +884,14 @@ int onerf_launch_field_bf16_two_tile(onerf_ctx* ctx, const FieldParams& fp, cuda
     if (sl.tile == 0 && last_slot_of_layer && sl.layer + 1 < n && P.layers[sl.layer + 1].nslab_x > 0) xgen(0, xi, 0xffu);
   }
   P.n_events = ne;
+  return ONERF_OK;
+}
+
+int onerf_launch_field_bf16_two_tile(onerf_ctx* ctx, const FieldParams& fp, cudaStream_t stream) {
+  const PackLayout& L = fp.L;
+  T2Params P;
+  const int rc = t2_build_program(fp, P);
+  if (rc != ONERF_OK) return rc;
   const int64_t total = (int64_t)fp.n_rays * fp.S;
   const int64_t tiles = (total + TM - 1) / TM, pairs = (tiles + 1) / 2;
   const int blocks = (int)(pairs < ctx->num_sms ? pairs : ctx->num_sms);
@@ -903,4 +911,37 @@ int onerf_launch_field_bf16_two_tile(onerf_ctx* ctx, const FieldParams& fp, cuda
   }
   ONERF_LAUNCH_CHECK(ctx);
   return ONERF_OK;
+}
+
+// Test hook (tests/test_two_tile_program_cpu.py, no GPU needed): the program the launcher would hand to the kernel.
+//   out[0..3] = n_slots, n_events, n_layers, words per slot (4 + 16)
+//   per slot  : tile, layer, half, flags (SlotFlags | accumulator << 4), then the 16 record words
+//   per event : the 4 ev_tab words, then ev_dump
+// Returns the number of words written, or a negative error code.
+extern "C" int onerf_debug_two_tile_program(int want_scene, int want_object, int train, uint32_t* out, int cap) {
+  FieldParams fp;
+  memset(&fp, 0, sizeof(fp));
+  fp.L = onerf_make_layout(1);
+  fp.want_scene = want_scene; fp.want_object = want_object;
+  fp.n_rays = 1024; fp.S = 128;
+  fp.train_ws = train ? reinterpret_cast<void*>(uintptr_t(1024)) : nullptr;   // only tested against null by the builder
+  T2Params* P = new T2Params;
+  const int rc = t2_build_program(fp, *P);
+  if (rc != ONERF_OK) { delete P; return rc < 0 ? rc : -rc; }
+  const int need = 4 + P->n_slots * 20 + P->n_events * 5;
+  if (need > cap) { delete P; return -need; }
+  int o = 0;
+  out[o++] = (uint32_t)P->n_slots; out[o++] = (uint32_t)P->n_events; out[o++] = (uint32_t)P->n_layers; out[o++] = 20u;
+  for (int i = 0; i < P->n_slots; ++i) {
+    out[o++] = P->slots[i].tile; out[o++] = P->slots[i].layer; out[o++] = P->slots[i].half; out[o++] = P->slots[i].flags;
+    for (int q = 0; q < 4; ++q) {
+      out[o++] = P->rec[i].q[q].x; out[o++] = P->rec[i].q[q].y; out[o++] = P->rec[i].q[q].z; out[o++] = P->rec[i].q[q].w;
+    }
+  }
+  for (int i = 0; i < P->n_events; ++i) {
+    out[o++] = P->ev_tab[i].x; out[o++] = P->ev_tab[i].y; out[o++] = P->ev_tab[i].z; out[o++] = P->ev_tab[i].w;
+    out[o++] = P->ev_dump[i];
+  }
+  delete P;
+  return o;
 }
