@@ -917,6 +917,7 @@ int onerf_launch_field_bf16_two_tile(onerf_ctx* ctx, const FieldParams& fp, cuda
 //   out[0..3] = n_slots, n_events, n_layers, words per slot (4 + 16)
 //   per slot  : tile, layer, half, flags (SlotFlags | accumulator << 4), then the 16 record words
 //   per event : the 4 ev_tab words, then ev_dump
+//   per layer : N, halves, X slabs, H slabs, ring stages per slot, groups[8] (what the weight producer walks)
 // Returns the number of words written, or a negative error code.
 extern "C" int onerf_debug_two_tile_program(int want_scene, int want_object, int train, uint32_t* out, int cap) {
   FieldParams fp;
@@ -928,7 +929,7 @@ extern "C" int onerf_debug_two_tile_program(int want_scene, int want_object, int
   T2Params* P = new T2Params;
   const int rc = t2_build_program(fp, *P);
   if (rc != ONERF_OK) { delete P; return rc < 0 ? rc : -rc; }
-  const int need = 4 + P->n_slots * 20 + P->n_events * 5;
+  const int need = 4 + P->n_slots * 20 + P->n_events * 5 + P->n_layers * (5 + T2_MAX_GROUPS);
   if (need > cap) { delete P; return -need; }
   int o = 0;
   out[o++] = (uint32_t)P->n_slots; out[o++] = (uint32_t)P->n_events; out[o++] = (uint32_t)P->n_layers; out[o++] = 20u;
@@ -941,6 +942,13 @@ extern "C" int onerf_debug_two_tile_program(int want_scene, int want_object, int
   for (int i = 0; i < P->n_events; ++i) {
     out[o++] = P->ev_tab[i].x; out[o++] = P->ev_tab[i].y; out[o++] = P->ev_tab[i].z; out[o++] = P->ev_tab[i].w;
     out[o++] = P->ev_dump[i];
+  }
+  // per layer, the producer's view of the same walk: N, halves, X slabs, H slabs, ring stages and their packed descriptions
+  for (int l = 0; l < P->n_layers; ++l) {
+    const T2Layer& t = P->layers[l];
+    out[o++] = (uint32_t)t.N; out[o++] = (uint32_t)t.nhalf; out[o++] = (uint32_t)t.nslab_x; out[o++] = (uint32_t)t.nslab_h;
+    out[o++] = (uint32_t)t.ngroups;
+    for (int g = 0; g < T2_MAX_GROUPS; ++g) out[o++] = (uint32_t)t.groups[g];
   }
   delete P;
   return o;

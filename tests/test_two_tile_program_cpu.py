@@ -44,7 +44,7 @@ def _program(want_scene, want_object, train):
         hdr, gmeta = rec[1], rec[2]
         ngroups = (hdr >> 20) & 0xff
         groups = [(gmeta >> (4 * g)) & 15 for g in range(ngroups)]
-        slots.append(dict(tile=tile, layer=layer, half=half, acc=flags >> 4, wait_h=bool(flags & SLOT_WAIT_H),
+        slots.append(dict(rec=rec, tile=tile, layer=layer, half=half, acc=flags >> 4, wait_h=bool(flags & SLOT_WAIT_H),
                           wait_xs=bool(flags & SLOT_WAIT_XS), reads_x=any(not (g >> 3) for g in groups),
                           reads_h=any(g >> 3 for g in groups), hdr=hdr, ngroups=ngroups,
                           rec_acc=(hdr >> 16) & 1, rec_tile=(hdr >> 17) & 1))
@@ -53,7 +53,16 @@ def _program(want_scene, want_object, train):
         x, y, z, ww, ed = w[o:o + 5]
         o += 5
         events.append(dict(x=x, w=ww, ed=ed))
+    layers = []
+    for _ in range(n_layers):
+        N, nhalf, nx, nh, ng = w[o:o + 5]
+        groups = w[o + 5:o + 5 + ng]
+        o += 5 + 8
+        layers.append(dict(N=N, nhalf=nhalf, nslab_x=nx, nslab_h=nh,
+                           groups=[dict(first=g & 31, cnt=(g >> 5) & 7, from_h=(g >> 8) & 1) for g in groups]))
     assert o == n
+    for s_ in slots:
+        s_["layer_info"] = layers[s_["layer"]]
     return slots, events, n_layers
 
 
@@ -254,3 +263,33 @@ def test_the_model_detects_broken_programs():
                 done += 1
             e["w"] = EV_XGEN | (xf << 8)
     assert caught(slots, ev) == 6
+
+
+def test_mma_records_and_the_weight_producer_walk_the_same_ring_stages():
+    """The MMA warp reads 64-byte slot records, the weight producer walks layers[].groups[]: two tables, one ring.  They must
+    describe the same stages in the same order, and the operand offsets in the records must be the ones the layouts imply."""
+    for cfg in [(1, 1, 0), (1, 0, 0), (0, 1, 0), (1, 1, 1)]:
+        slots, events, n_layers = _program(*cfg)
+        for s in slots:
+            L, rec = s["layer_info"], s["rec"]
+            half_n = L["N"] >> (L["nhalf"] - 1)
+            assert rec[0] == (1 << 4) | (1 << 7) | (1 << 10) | ((half_n >> 3) << 17) | ((128 >> 4) << 24)     # instruction descriptor
+            assert (rec[1] & 0xffff) == (half_n * 64) >> 4                                                    # bytes of one slab of this half / 16
+            assert s["ngroups"] == len(L["groups"]) <= 5
+            x_slabs, h_slabs = [], []
+            for g, G in enumerate(L["groups"]):
+                meta = (rec[2] >> (4 * g)) & 15
+                assert (meta & 7) == G["cnt"] and (meta >> 3) == G["from_h"] and 1 <= G["cnt"] <= 4
+                for i in range(G["cnt"]):
+                    slab = G["first"] + i
+                    rel = (rec[4 + 2 * g + (i >> 1)] >> (16 * (i & 1))) & 0xffff
+                    if G["from_h"]:
+                        assert rel == 16 * slab                         # TMEM columns: 32 bf16 of K = 16 packed columns
+                        h_slabs.append(slab)
+                    else:
+                        assert rel == (slab >> 1) * 1024 + (slab & 1) * 4   # SWIZZLE_128B atoms of 64 K: 16-byte units
+                        x_slabs.append(slab)
+            assert x_slabs == list(range(L["nslab_x"])) and h_slabs == list(range(L["nslab_h"]))
+            assert s["reads_x"] == (L["nslab_x"] > 0) and s["reads_h"] == (L["nslab_h"] > 0)
+            assert s["wait_h"] == (L["nslab_h"] > 0 and s["half"] == 0)
+            assert s["wait_xs"] == (L["nslab_x"] > 0 and s["half"] == 0)
